@@ -1,0 +1,43 @@
+// Shared helpers for the cgat_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/cgat_b200.h"
+
+namespace cgat {
+
+extern thread_local char g_err[512];
+extern long long g_launches;
+
+inline int fail(int code, const char* what) {
+  snprintf(g_err, sizeof(g_err), "%s (code %d)", what, code);
+  return code ? code : -1;
+}
+
+inline int check_launch(const char* name) {
+  ++g_launches;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    snprintf(g_err, sizeof(g_err), "%s: %s", name, cudaGetErrorString(e));
+    return (int)e;
+  }
+  return 0;
+}
+
+#define CGAT_CUDA(expr)                                                     \
+  do {                                                                      \
+    cudaError_t _e = (expr);                                                \
+    if (_e != cudaSuccess) {                                                \
+      snprintf(cgat::g_err, sizeof(cgat::g_err), "%s: %s", #expr,           \
+               cudaGetErrorString(_e));                                     \
+      return (int)_e;                                                       \
+    }                                                                       \
+  } while (0)
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+__host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace cgat

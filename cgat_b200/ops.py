@@ -1,0 +1,116 @@
+"""autograd.Functions over the C ABI (include/cgat_b200.h).  Host glue only: every Function
+allocates outputs, calls one or more kernels on the current stream, and wires the hand-written
+backward kernels into autograd.  No CPU path."""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .graph import SegmentPlan
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        raise TypeError("cgat_b200 kernels are fp32")
+    return t.contiguous()
+
+
+class _SegSoftmax(torch.autograd.Function):
+    """out[s,h,:] = sum_{t in seg s} alpha[t,h,:] * value[t,h,:],
+    alpha = u * exp(gate - segmax) / (segsum(u * exp(gate - segmax)) + eps).
+
+    Replaces torch_geometric.utils.softmax + scatter_add (reference CGAT/CGAT.py:59-61, :323-326)
+    and scatter_max / scatter_add in WeightedAttention (reference CGAT/roost_message.py:307-315)."""
+
+    @staticmethod
+    def forward(ctx, gate, value, u, ptr, seg_of_row, n_seg, eps):
+        gate, value = _f32c(gate), _f32c(value)
+        u = None if u is None else _f32c(u)
+        n_rows, heads, f = value.shape
+        fa = gate.shape[2]
+        out = torch.empty((n_seg, heads, f), dtype=torch.float32, device=value.device)
+        smax = torch.empty((n_seg, heads, fa), dtype=torch.float32, device=value.device)
+        sden = torch.empty_like(smax)
+        _lib.call("cgat_seg_softmax_fwd", _lib.ptr(gate), _lib.ptr(value), _lib.ptr(u), _lib.ptr(ptr), n_seg,
+                  heads, f, fa, eps, _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.stream())
+        ctx.save_for_backward(gate, value, u, seg_of_row, out, smax, sden)
+        ctx.eps = eps
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        gate, value, u, seg_of_row, out, smax, sden = ctx.saved_tensors
+        d_out = _f32c(d_out)
+        n_rows, heads, f = value.shape
+        fa = gate.shape[2]
+        d_gate = torch.empty_like(gate)
+        d_value = torch.empty_like(value)
+        _lib.call("cgat_seg_softmax_bwd", _lib.ptr(gate), _lib.ptr(value), _lib.ptr(u), _lib.ptr(seg_of_row),
+                  _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(d_out), n_rows, heads, f, fa,
+                  ctx.eps, _lib.ptr(d_gate), _lib.ptr(d_value), _lib.stream())
+        d_u = None
+        if u is not None and ctx.needs_input_grad[2]:
+            # alpha ∝ exp(gate + log u)  =>  dL/du = (dL/dgate summed over heads/channels) / u
+            d_u = d_gate.sum(dim=(1, 2)) / u
+        return d_gate, d_value, d_u, None, None, None, None
+
+
+def seg_softmax(gate, value, plan: SegmentPlan | None = None, *, ptr=None, seg_of_row=None, n_seg=None,
+                u=None, eps=1e-16):
+    """gate (n,H,Fa), value (n,H,F) -> (n_seg,H,F).  Either a SegmentPlan or (ptr, seg_of_row, n_seg)."""
+    if plan is not None:
+        ptr, seg_of_row, n_seg = plan.ptr, plan.index, plan.n_seg
+    return _SegSoftmax.apply(gate, value, u, ptr, seg_of_row, n_seg, float(eps))
+
+
+# ----------------------------------------------------------------------------------------------
+# Dense pieces.  Stage A: library GEMMs (torch / cuBLAS fp32, TF32 disabled by torch default) with
+# the hand-written segment kernels in between.  The fused sm_100a kernels replace these one by one.
+# ----------------------------------------------------------------------------------------------
+LEAKY_SLOPE = 0.01
+
+
+def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
+    """fea (n,In) -> (n,H,Out): per head h  W2_h leaky_relu(W1_h fea + b1_h) + b2_h
+    (reference MultiHeadNetwork.forward, CGAT/CGAT.py:103-109)."""
+    n = fea.shape[0]
+    out_dim, hd = w_out.shape[1], w_out.shape[2]
+    hid = torch.nn.functional.leaky_relu(torch.addmm(b_in, fea, w_in.t()), LEAKY_SLOPE)      # (n, H*Hd)
+    hid = hid.view(n, heads, hd).transpose(0, 1)                                              # (H, n, Hd)
+    out = torch.baddbmm(b_out.view(heads, 1, out_dim), hid, w_out.transpose(1, 2))            # (H, n, Out)
+    return out.transpose(0, 1)                                                                # (n, H, Out)
+
+
+def edge_attention(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
+    """Node-attention aggregation, reference CGAT/CGAT.py:319-329 (Appendix A of SURVEY.md).
+
+    m_t = [x[dst]; e(rank_t); x[src]]; the first MLP layer is linear in m_t, so it is evaluated per
+    atom and per rank and only summed per edge:  W1 m_t = (x W1_i^T)[dst] + (e W1_e^T + b1)[rank] + (x W1_j^T)[src].
+    Edges are visited in destination-sorted order (plan)."""
+    n, f = x.shape
+    fe = edge_table.shape[1]
+    hhd = w1a.shape[0]
+    hd = hhd // heads
+    w1 = torch.cat([w1a, w1m], dim=0)                              # (2*H*Hd, 2F+Fe)
+    p_dst = x @ w1[:, :f].t()                                      # (N, 2*H*Hd)
+    p_src = x @ w1[:, f + fe:].t()
+    t_rank = torch.addmm(torch.cat([b1a, b1m]), edge_table, w1[:, f:f + fe].t())   # (K+1, 2*H*Hd)
+    pre = p_dst.index_select(0, plan.dst) + p_src.index_select(0, plan.src) + t_rank.index_select(0, plan.rank)
+    hid = torch.nn.functional.leaky_relu(pre, LEAKY_SLOPE)
+    e = hid.shape[0]
+    hid_a = hid[:, :hhd].view(e, heads, hd).transpose(0, 1)        # (H, E, Hd)
+    hid_m = hid[:, hhd:].view(e, heads, hd).transpose(0, 1)
+    gate = torch.baddbmm(b2a.view(heads, 1, -1), hid_a, w2a.transpose(1, 2)).transpose(0, 1).contiguous()
+    msg = torch.baddbmm(b2m.view(heads, 1, -1), hid_m, w2m.transpose(1, 2)).transpose(0, 1).contiguous()
+    agg = seg_softmax(gate, msg, ptr=plan.rowptr, seg_of_row=plan.dst, n_seg=n, eps=1e-16)   # (N,H,F)
+    return agg.mean(dim=1)
+
+
+def hyper_linear(z, weight, bias, y, out_ch):
+    """y_out[n] = reshape(weight z[n] + bias)[:out*in] y[n] + (...)[out*in:]
+    (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209)."""
+    in_ch = y.shape[1]
+    p = torch.addmm(bias, z, weight.t())                            # (N, out*in + out)
+    w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
+    b = p[:, in_ch * out_ch:]
+    return torch.baddbmm(b.unsqueeze(2), w, y.unsqueeze(2)).squeeze(2)

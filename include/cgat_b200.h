@@ -1,0 +1,74 @@
+/*
+ * cgat_b200 — C ABI of the B200-native CGAT hot path.
+ *
+ * The reference (hyllios/CGAT) is pure Python and has NO FFI: its model is selected by module name
+ * (CGAT/lightning_module.py:165-176, `importlib.import_module(hparams.version).CGAtNet`).  The
+ * drop-in boundary is therefore the Python class `cgat_b200.CGAT.CGAtNet`; this header is the
+ * compute boundary underneath it.  Each entry point replaces the implicit third-party GPU work the
+ * reference dispatches at the cited call site.
+ *
+ * Conventions: plain device pointers + sizes, an explicit CUDA stream (cudaStream_t passed as
+ * void*), no allocation inside, no exceptions across the ABI.  Every function returns 0 on success
+ * or a non-zero cudaError_t / negative argument-error code; cgat_last_error() gives the message.
+ * All floating point is fp32; all indices are int64 at the Python boundary and int32 after
+ * cgat_csr_build / cgat_segment_ptr.
+ */
+#ifndef CGAT_B200_H_
+#define CGAT_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGAT_B200_ABI_VERSION 1
+
+int cgat_abi_version(void);
+const char* cgat_last_error(void);
+/* number of kernels launched by this library since load (bench.py's `gpu_launches`) */
+int64_t cgat_launch_count(void);
+
+/* ---- integer structure -------------------------------------------------
+ * Replaces what PyG's MessagePassing.propagate / torch_scatter derive implicitly from edge_index
+ * on every call (reference CGAT/CGAT.py:313-326): a CSR-by-destination view of the edge list.
+ *   edge_index : (2,E) int64, row 0 = source, row 1 = destination   (CGAT/data.py:140)
+ *   edge_attr  : (E,)  int64 shell rank                               (CGAT/prepare_data.py:163-169)
+ * Outputs (int32): perm (E) = stable argsort of destinations, rowptr (N+1) = exclusive cumsum of
+ * in-degrees, and the permuted src / dst / rank arrays.  Bit-exact vs torch.sort(stable=True),
+ * bincount, cumsum.  workspace: >= cgat_csr_workspace_bytes(E,N) bytes.                           */
+size_t cgat_csr_workspace_bytes(int64_t n_edges, int64_t n_nodes);
+int cgat_csr_build(const int64_t* edge_index, const int64_t* edge_attr, int64_t n_edges, int64_t n_nodes,
+                   int32_t* perm, int32_t* rowptr, int32_t* src_sorted, int32_t* dst_sorted,
+                   int32_t* rank_sorted, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ptr (n_seg+1) of a SORTED int64 segment index vector: crystal_ptr from batch.batch
+ * (CGAT/CGAT.py:567), Roost row pointers from self_fea_idx / crystal_elem_idx
+ * (CGAT/roost_message.py:445-453).  Also writes the index as int32.                              */
+int cgat_segment_ptr(const int64_t* index, int64_t n, int64_t n_seg, int32_t* ptr, int32_t* index32,
+                     void* stream);
+
+/* ---- segmented softmax + weighted sum ---------------------
+ * One kernel family replaces torch_geometric.utils.softmax + scatter_add at CGAT/CGAT.py:323-326
+ * and :59-61, and scatter_max/scatter_add at CGAT/roost_message.py:307-315.
+ * Rows t of segment s are contiguous: [ptr[s], ptr[s+1]).
+ *   gate  (n_rows, H, Fa)  Fa == F (vector attention) or 1 (scalar attention)
+ *   value (n_rows, H, F)
+ *   u     (n_rows) optional per-row multiplier (Roost weights**pow), may be NULL
+ *   alpha = u * exp(gate - segmax(gate)) / (segsum(u * exp(gate - segmax)) + eps)
+ *   out   (n_seg, H, F) = segsum(alpha * value);   atomic-free, deterministic.
+ * Saved for backward: seg_max, seg_den (n_seg, H, Fa).                                           */
+int cgat_seg_softmax_fwd(const float* gate, const float* value, const float* u, const int32_t* ptr,
+                         int64_t n_seg, int32_t heads, int32_t f, int32_t fa, float eps,
+                         float* out, float* seg_max, float* seg_den, void* stream);
+/* d_gate (n_rows,H,Fa), d_value (n_rows,H,F) from d_out (n_seg,H,F).  d_gate is also d(log u). */
+int cgat_seg_softmax_bwd(const float* gate, const float* value, const float* u, const int32_t* seg_of_row,
+                         const float* out, const float* seg_max, const float* seg_den, const float* d_out,
+                         int64_t n_rows, int32_t heads, int32_t f, int32_t fa, float eps,
+                         float* d_gate, float* d_value, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGAT_B200_H_ */

@@ -1,0 +1,68 @@
+"""Shared case table for the golden fixtures (mirrors oracle/make_golden.py:CASES; the fixtures
+themselves record the parameter names/shapes, which the tests cross-check)."""
+import os
+
+import numpy as np
+import torch
+
+from cgat_b200 import synthetic, weights
+
+CASES = {
+    "default_k12": (dict(elem_fea_len=128, n_graph=5, msg_heads=5, neighbor_number=12, mean_pooling=False,
+                         rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
+                         n_graph_roost=3),
+                    dict(n_crystals=12, max_nbr=12, seed=0), 0),
+    "default_k24": (dict(elem_fea_len=128, n_graph=5, msg_heads=5, neighbor_number=24, mean_pooling=False,
+                         rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
+                         n_graph_roost=3),
+                    dict(n_crystals=6, max_nbr=24, seed=1), 1),
+    "scalar_attn_meanpool": (dict(elem_fea_len=64, n_graph=3, msg_heads=3, neighbor_number=12, mean_pooling=True,
+                                  rezero=False, update_edges=True, vector_attention=False,
+                                  global_vector_attention=False, n_graph_roost=2),
+                             dict(n_crystals=16, max_nbr=12, seed=2), 2),
+    "mixed_flags": (dict(elem_fea_len=32, n_graph=2, msg_heads=4, neighbor_number=8, mean_pooling=False,
+                         rezero=True, update_edges=True, vector_attention=True, global_vector_attention=False,
+                         n_graph_roost=1),
+                    dict(n_crystals=20, max_nbr=8, seed=3), 3),
+    "large_cell_k24": (dict(elem_fea_len=32, n_graph=2, msg_heads=2, neighbor_number=24, mean_pooling=False,
+                            rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
+                            n_graph_roost=3),
+                       dict(n_crystals=2, max_nbr=24, seed=4, atoms_lo=200, atoms_hi=256), 4),
+}
+
+ATOL, RTOL = 1e-4, 1e-3  # BASELINE.json north_star: fp32 predictions and gradients
+
+
+def load_golden(golden_dir, name):
+    return np.load(os.path.join(golden_dir, f"ref_{name}.npz"))
+
+
+def golden_shapes(gold):
+    return {str(k): tuple(int(x) for x in str(s).split(",") if x) for k, s in
+            zip(gold["state_names"], gold["state_shapes"])}
+
+
+def oracle_cfg(mkw):
+    return dict(n_graph=mkw["n_graph"], msg_heads=mkw["msg_heads"], mean_pooling=mkw["mean_pooling"],
+                rezero=mkw["rezero"])
+
+
+def training_scalar(out, y):
+    """The scalar make_golden.py differentiates (L1 on column 0, reference lightning_module.py:237-240)."""
+    target = y.view(-1, 1) / y.abs().max()
+    return (out[:, :1] - target).abs().mean() + 0.1 * out[:, 1].mean()
+
+
+def assert_close(a, b, what, atol=ATOL, rtol=RTOL):
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    assert a.shape == b.shape, f"{what}: shape {tuple(a.shape)} vs {tuple(b.shape)}"
+    err = (a - b).abs()
+    bad = err > atol + rtol * b.abs()
+    assert not bad.any(), (f"{what}: {int(bad.sum())}/{bad.numel()} out of tolerance, max abs err "
+                           f"{err.max().item():.3e} (ref max {b.abs().max().item():.3e})")
+
+
+def grad_digest(t):
+    g = t.double()
+    return [g.sum().item(), g.abs().sum().item(), g.pow(2).sum().sqrt().item()]
