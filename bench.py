@@ -1,0 +1,355 @@
+#!/usr/bin/env python
+"""bench.py — CGAtNet train step (default) or screening inference on N B200s; one JSON line on rank 0.
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                       # cfg2: train step, 500 crystals / GPU
+    python bench.py --workload cfg3_infer                                # 5000-crystal no_grad batches
+    python -m torch.distributed.run --nproc-per-node 8 ... bench.py --gpus 8 ...
+    python bench.py --impl reference                                     # the reference's CPU path (oracle port)
+
+Metric: crystals/s (BASELINE.json).  `value` = device-resident inputs; `e2e` = the same step through
+CGAtNet.forward with pinned HOST batches copied in and the loss read back inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DEFAULT_NET = dict(elem_fea_len=128, n_graph=5, msg_heads=5, mean_pooling=False, rezero=True, update_edges=True,
+                   vector_attention=True, global_vector_attention=True, n_graph_roost=3)
+WORKLOADS = {
+    # BASELINE.json configs[1]: default config training step, batch 500 crystals, fp32, K=12 (SURVEY §8d cfg mapping)
+    "cfg2_train": dict(crystals=500, max_nbr=12, train=True, atoms=(2, 20), net={}),
+    # configs[2]: screening inference, batches of 5000 (reference CGAT/predict.py:20)
+    "cfg3_infer": dict(crystals=5000, max_nbr=12, train=False, atoms=(2, 20), net={}),
+    # configs[4]: large cells, 24 neighbours
+    "cfg5_large": dict(crystals=12, max_nbr=24, train=True, atoms=(200, 256), net={}),
+    # configs[3]: wider/deeper net
+    "cfg4_wide": dict(crystals=500, max_nbr=12, train=True, atoms=(2, 20),
+                      net=dict(elem_fea_len=256, msg_heads=8, n_graph=5)),
+}
+LR, WD = 1.25e-4, 1e-6  # reference lightning_module.py:499-533 defaults
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], bf16=p["bf16_tflops"], bf16_sustained=p["bf16_tflops_sustained"],
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v == "Active"})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=reasons, samples=len(sm))
+
+
+# ------------------------------------------------------------------------------------------------
+def build_net(wl):
+    import cgat_b200
+    kw = dict(DEFAULT_NET)
+    kw.update(wl["net"])
+    kw["neighbor_number"] = wl["max_nbr"]
+    return cgat_b200.CGAtNet(200, **kw), kw
+
+
+def make_pool(wl, rank, n=4):
+    from cgat_b200 import synthetic
+    lo, hi = wl["atoms"]
+    return [synthetic.make_batch(wl["crystals"], wl["max_nbr"], seed=1000 * rank + 1 + i, atoms_lo=lo, atoms_hi=hi)
+            for i in range(n)]
+
+
+def target_norm(sb, dev):
+    y = sb.graph.y
+    return ((y - y.mean()) / (y.std() + 1e-6)).view(-1, 1).to(dev)
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from cgat_b200 import _lib, distributed as cdist
+    wl = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.manual_seed(0)  # same initial weights on every rank (DDP broadcast equivalent)
+    model, net_kw = build_net(wl)
+    model = model.to(dev)
+    train = wl["train"]
+    pool = make_pool(wl, rank)
+    dev_pool = [sb.to(dev) for sb in pool]
+    pin_pool = [sb.pin_memory() for sb in pool]
+    targets = [target_norm(sb, dev) for sb in pool]
+    sync = cdist.GradSync(model, world) if train else None
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=LR, weight_decay=WD, fused=True) if train else None
+    crit = torch.nn.L1Loss()
+
+    def step(sb, tgt):
+        if train:
+            out = model(sb.graph, sb.roost)
+            loss = crit(out[:, :1], tgt)                     # reference lightning_module.py:237-240
+            loss.backward()
+            sync.all_reduce()
+            opt.step()
+            sync.zero_grad()
+            return loss
+        with torch.no_grad():
+            return model(sb.graph, sb.roost)
+
+    def e2e_step(i):
+        sb = pin_pool[i % len(pin_pool)].to(dev, non_blocking=True)
+        res = step(sb, targets[i % len(pool)])
+        return float(res) if train else res[:, 0].cpu()     # device -> host read of the step's result
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            fn(i)
+        t1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    resident = lambda i: step(dev_pool[i % len(pool)], targets[i % len(pool)])
+    for i in range(args.warmup):
+        resident(i)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = _lib.launch_count()
+    ms = timed(resident, args.steps)
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(min(args.warmup, 2)):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    crystals = wl["crystals"] * world
+    value = crystals * args.steps / (ms / 1e3)
+    e2e_value = crystals * args.steps / (ms_e2e / 1e3)
+    h2d = pool[0].nbytes()
+    d2h = 4 if train else wl["crystals"] * 4
+
+    roof = cpu = None
+    if rank == 0:
+        roof = roofline(model, dev_pool[0], targets[0], train, step, args)
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(wl, net_kw, train)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n_atoms = int(sum(int(sb.n_atoms.sum()) for sb in pool) / len(pool))
+    line = {
+        "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),
+        "value": round(value, 2), "unit": "crystals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: CGAtNet default hyper-parameters "
+                               f"(F={net_kw['elem_fea_len']}, heads={net_kw['msg_heads']}, layers={net_kw['n_graph']}, "
+                               f"vector attention, edge updates, ReZero, concat pooling), {wl['crystals']} synthetic "
+                               f"crystals per GPU per step, {wl['max_nbr']} neighbours, ~{n_atoms} atoms / "
+                               f"{n_atoms * wl['max_nbr']} edges per step, fp32"
+                               + (", L1 loss + AdamW" if train else ", no_grad"),
+                   "crystals_per_gpu": wl["crystals"], "max_nbr": wl["max_nbr"],
+                   "l2": "rotating pool of 4 distinct batches; per-step working set (249 MB weights + 498 MB AdamW "
+                         "state + >1 GB activations) exceeds the 126 MB L2",
+                   "parallelism": f"dp{world}" if train else f"shard{world}"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": "crystals/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 4)},
+        "gpu_launches": launches,
+        "roofline": roof,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(line))
+
+
+def roofline(model, sb, tgt, train, step, args):
+    """Per-launch CUDA-event timing of this library's kernels over extra (untimed) steps; reports the
+    kernel with the largest share.  Algorithmic bytes / flops per launch are declared by the ops."""
+    from cgat_b200 import _lib
+    pk = peaks()
+    _lib.profile_begin()
+    n = max(2, min(args.steps, 4))
+    for _ in range(n):
+        step(sb, tgt)
+    rows = _lib.profile_end()
+    if not rows:
+        return None
+    total = sum(r["ms"] for r in rows.values())
+    name, top = max(rows.items(), key=lambda kv: kv[1]["ms"])
+    avg_ms = top["ms"] / top["launches"]
+    bound = top["bound"]
+    if bound == "tensor":
+        achieved = top["flops"] / top["launches"] / (avg_ms * 1e-3) / 1e12
+        peak, unit = pk["bf16_sustained"], "TFLOP/s"
+    else:
+        achieved = top["bytes"] / top["launches"] / (avg_ms * 1e-3) / 1e9
+        peak, unit = pk["hbm"], "GB/s"
+    return {"kernel": name, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
+            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": pk["source"],
+            "avg_launch_ms": round(avg_ms, 5), "share_of_own_kernel_time": round(top["ms"] / total, 4),
+            "own_kernels_ms_per_step": round(total / n, 4),
+            "note": top.get("note", "")}
+
+
+# ------------------------------------------------------------------------------------------------
+def oracle_train_state(net_kw, seed=0):
+    """Reference-compatible parameters for the oracle port (shapes from this package's module tree)."""
+    import cgat_b200
+    from cgat_b200 import weights
+    model = cgat_b200.CGAtNet(200, **net_kw)
+    sd = weights.seeded_state_dict({k: v.shape for k, v in model.state_dict().items()}, seed)
+    for v in sd.values():
+        v.requires_grad_(True)
+    return sd
+
+
+def oracle_step_fn(wl, net_kw, train, n_crystals):
+    from cgat_b200 import synthetic
+    from oracle import cgat_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    sd = oracle_train_state(net_kw)
+    cfg = dict(n_graph=net_kw["n_graph"], msg_heads=net_kw["msg_heads"], mean_pooling=net_kw["mean_pooling"],
+               rezero=net_kw["rezero"])
+    lo, hi = wl["atoms"]
+    pool = [synthetic.make_batch(n_crystals, wl["max_nbr"], seed=1 + i, atoms_lo=lo, atoms_hi=hi) for i in range(2)]
+    opt = torch.optim.AdamW(list(sd.values()), lr=LR, weight_decay=WD) if train else None
+
+    def step(i):
+        sb = pool[i % 2]
+        if train:
+            out = O.cgat_forward(sd, cfg, sb.graph, sb.roost, as_written=True)
+            y = sb.graph.y
+            loss = (out[:, :1] - ((y - y.mean()) / (y.std() + 1e-6)).view(-1, 1)).abs().mean()
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return float(loss)
+        with torch.no_grad():
+            return O.cgat_forward(sd, cfg, sb.graph, sb.roost, as_written=True)
+    return step
+
+
+def cpu_baseline(wl, net_kw, train):
+    """The reference's CPU path (oracle port of the unmodified modules, dead Edge attention included,
+    'as written') on this box's host cores, on a bounded sample of the same workload."""
+    n = min(64, wl["crystals"])  # the reference's default --batch-size
+    step = oracle_step_fn(wl, net_kw, train, n)
+    step(0)
+    best = 1e30
+    for i in range(2):
+        t = time.perf_counter()
+        step(i + 1)
+        best = min(best, time.perf_counter() - t)
+    return {"value": round(n / best, 3), "unit": "crystals/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} crystals per step ({'fwd+bwd+AdamW' if train else 'forward'}), best of 2 after 1 warm-up, "
+                      "oracle port of the reference modules incl. its dead Edge attention"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference
+    is pure Python needing torch_geometric/torch_scatter, which are not installable here) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    kw = dict(DEFAULT_NET)
+    kw.update(wl["net"])
+    kw["neighbor_number"] = wl["max_nbr"]
+    train = wl["train"]
+    n = min(64, wl["crystals"])
+    step = oracle_step_fn(wl, kw, train, n)
+    for i in range(args.warmup):
+        step(i)
+    t = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    dt = time.perf_counter() - t
+    value = n * args.steps / dt
+    sample = (f"{n} crystals per step (the reference's default batch size) of the {args.workload} workload, "
+              f"{'fwd+bwd+AdamW' if train else 'forward'} on CPU")
+    print(json.dumps({
+        "impl": "reference",
+        "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),
+        "value": round(value, 3), "unit": "crystals/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "sample": sample},
+        "cpu_baseline": {"value": round(value, 3), "unit": "crystals/s", "cores": os.cpu_count(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": round(value, 3), "unit": "crystals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2_train", choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

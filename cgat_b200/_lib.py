@@ -28,6 +28,7 @@ SIGNATURES = {
     "cgat_seg_softmax_fwd": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _F32, _P, _P, _P, _P]),
     "cgat_seg_softmax_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F32,
                                             _P, _P, _P]),
+    "cgat_gemm3x_nt": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I32, _P]),
 }
 
 
@@ -67,11 +68,45 @@ def stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def call(name, *args):
+_prof = None  # list of (key, start_event, end_event, work) while profiling
+
+
+def call(name, *args, work=None):
+    """Invoke one C-ABI entry point on the current stream.  `work` (optional) declares the
+    algorithmic bytes / flops of this launch for bench.py's roofline:
+    dict(key=..., bound='hbm'|'tensor', bytes=..., flops=..., note=...)."""
     lib = load()
+    if _prof is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
     rc = getattr(lib, name)(*args)
+    if _prof is not None:
+        e1.record()
+        _prof.append((name, e0, e1, work or {}))
     if rc != 0:
         raise CgatLibraryError(f"{name} failed: {lib.cgat_last_error().decode()}")
+
+
+def profile_begin():
+    global _prof
+    _prof = []
+
+
+def profile_end():
+    """-> {key: dict(ms, launches, bytes, flops, bound, note)} summed over the profiled launches."""
+    global _prof
+    rows, rec = {}, _prof
+    _prof = None
+    torch.cuda.synchronize()
+    for name, e0, e1, work in rec:
+        key = work.get("key", name)
+        r = rows.setdefault(key, dict(ms=0.0, launches=0, bytes=0.0, flops=0.0, bound=work.get("bound", "hbm"),
+                                      note=work.get("note", "")))
+        r["ms"] += e0.elapsed_time(e1)
+        r["launches"] += 1
+        r["bytes"] += float(work.get("bytes", 0))
+        r["flops"] += float(work.get("flops", 0))
+    return rows
 
 
 def launch_count():

@@ -1,0 +1,208 @@
+// cgat_gemm3x_nt: C[M,N] = act(A[M,K] · B[N,K]^T + bias), fp32 in / fp32 out, on the 5th-gen tensor
+// cores (tcgen05.mma kind::tf32, accumulators in TMEM) with error compensation: every operand is
+// split into tf32 hi/lo parts while it is staged into shared memory and three MMA passes
+// (lo·hi + hi·lo + hi·hi) reproduce the fp32 product to ~2^-21 relative.
+//
+// This is the building block of the dense pieces of the CGAT hot path that are plain matrix
+// products: the per-atom first-layer projections x·W1_i^T / x·W1_j^T (reference CGAT/CGAT.py:320-322
+// after the split described in cgat_b200/CGAT.py), the hypernetwork trunk layers (reference
+// CGAT/Hypernetworksmp.py:36-83) and their transposes in backward.
+//
+// Structure (one 128 x BN output tile per CTA):
+//   warps 0-3  producers: global -> registers (float4, coalesced) -> hi/lo split -> shared memory in
+//              the canonical K-major SWIZZLE_128B UMMA layout; then the epilogue (tcgen05.ld ->
+//              bias/activation -> global)
+//   warp  4    allocates TMEM and issues the MMAs from one thread; tcgen05.commit releases stages
+//   kStages-deep ring of (A_hi, A_lo, B_hi, B_lo) K-chunks of 32 floats, full/empty mbarriers.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cgat {
+namespace {
+
+using namespace tc;
+
+constexpr int kBM = 128;       // rows of the output tile = TMEM lanes
+constexpr int kKC = 32;        // K floats per chunk = one 128-byte swizzle row
+constexpr int kWorkers = 128;  // producer / epilogue threads
+constexpr int kThreads = kWorkers + 32;
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int kStages = (BN <= 128) ? 3 : 2;
+  static constexpr int kABytes = kBM * kKC * 4;  // 16 KB
+  static constexpr int kBBytes = BN * kKC * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kBBytes;
+  static constexpr int kBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  switch (act) {
+    case 1: return v > 0.f ? v : 0.01f * v;
+    case 2: return tanhf(v);
+    case 3: return fmaxf(v, 0.f);
+    default: return v;
+  }
+}
+
+// stage a [rows x 32] fp32 chunk (row-major source with leading dimension ld) as hi/lo SW128 tiles
+template <int ROWS>
+__device__ __forceinline__ void stage_chunk(const float* __restrict__ src, int64_t ld, int row0, int n_rows,
+                                            int k0, int k_total, uint8_t* hi, uint8_t* lo, int tid) {
+  constexpr int kIters = ROWS * 8 / kWorkers;
+  float4 v[kIters];
+#pragma unroll
+  for (int j = 0; j < kIters; ++j) {
+    int idx = tid + kWorkers * j;
+    int r = idx >> 3, c = idx & 7;
+    int gr = row0 + r, gk = k0 + c * 4;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr < n_rows && gk < k_total) v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)gr * ld + gk));
+  }
+#pragma unroll
+  for (int j = 0; j < kIters; ++j) {
+    int idx = tid + kWorkers * j;
+    uint32_t off = sw128_offset(idx >> 3, idx & 7);
+    float4 h, l;
+    split_tf32(v[j], h, l);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                 const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int act) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base_u32 = smem_u32(smem_raw);
+  uint8_t* smem = smem_raw + ((1024u - (base_u32 & 1023u)) & 1023u);  // SWIZZLE_128B needs 1024-B alignment
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kStages * S::kStageBytes);
+  uint64_t* full = bars;                  // [kStages]  producers -> MMA
+  uint64_t* empty = bars + S::kStages;    // [kStages]  MMA -> producers
+  uint64_t* accum = bars + 2 * S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * S::kStages + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
+  const int nk = (K + kKC - 1) / kKC;
+
+  if (tid == 0) {
+    for (int s = 0; s < S::kStages; ++s) {
+      mbar_init(&full[s], kWorkers);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, BN);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ---------------- producers ----------------
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % S::kStages, u = kc / S::kStages;
+      mbar_wait(&empty[s], (u + 1) & 1);  // passes immediately on the first use of a stage
+      uint8_t* st = smem + s * S::kStageBytes;
+      stage_chunk<kBM>(A, lda, m0, M, kc * kKC, K, st, st + S::kABytes, tid);
+      stage_chunk<BN>(B, ldb, n0, N, kc * kKC, K, st + 2 * S::kABytes, st + 2 * S::kABytes + S::kBBytes, tid);
+      fence_async_smem();
+      mbar_arrive(&full[s]);
+    }
+    // ---------------- epilogue ----------------
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll 1
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+      tmem_ld_wait();
+      const int nb = n0 + cc * 32;
+      if (m < M) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          int n = nb + j;
+          float b = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
+          v[j] = apply_act(v[j] + b, act);
+        }
+        float* crow = C + (int64_t)m * ldc + nb;
+        if (vec_ok && nb + 32 <= N) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nb + j < N) crow[j] = v[j];
+        }
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ---------------- MMA issuer ----------------
+    constexpr uint32_t idesc = umma_idesc_tf32(kBM, BN);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % S::kStages, u = kc / S::kStages;
+      mbar_wait(&full[s], u & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * S::kStageBytes);
+        const uint32_t a_lo = a_hi + S::kABytes;
+        const uint32_t b_hi = a_hi + 2 * S::kABytes;
+        const uint32_t b_lo = b_hi + S::kBBytes;
+#pragma unroll
+        for (int ks = 0; ks < kKC / 8; ++ks) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
+          const uint32_t o = ks * 32;
+          umma_tf32(tmem, umma_desc_k_sw128(a_lo + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
+          umma_tf32(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_lo + o), idesc, 1);
+          umma_tf32(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_hi + o), idesc, 1);
+        }
+        umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
+        if (kc == nk - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, BN);
+  }
+}
+
+template <int BN>
+int launch_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
+                int M, int N, int K, int act, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(gemm3x_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, kBM));
+  gemm3x_nt_kernel<BN><<<grid, kThreads, S::kBytes, stream>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, act);
+  return check_launch("gemm3x_nt_kernel");
+}
+
+}  // namespace
+}  // namespace cgat
+
+using namespace cgat;
+
+extern "C" int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                              int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M <= 0 || N <= 0) return 0;
+  if (K <= 0 || (K & 3) || (lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15))
+    return fail(-2, "cgat_gemm3x_nt: K, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return fail(-2, "cgat_gemm3x_nt: size overflow");
+  if (N <= 64) return launch_gemm<64>(A, lda, B, ldb, bias, C, ldc, (int)M, (int)N, (int)K, act, stream);
+  return launch_gemm<128>(A, lda, B, ldb, bias, C, ldc, (int)M, (int)N, (int)K, act, stream);
+}

@@ -32,7 +32,10 @@ class _SegSoftmax(torch.autograd.Function):
         smax = torch.empty((n_seg, heads, fa), dtype=torch.float32, device=value.device)
         sden = torch.empty_like(smax)
         _lib.call("cgat_seg_softmax_fwd", _lib.ptr(gate), _lib.ptr(value), _lib.ptr(u), _lib.ptr(ptr), n_seg,
-                  heads, f, fa, eps, _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.stream())
+                  heads, f, fa, eps, _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.stream(),
+                  work=dict(key="seg_softmax_fwd", bound="hbm",
+                            bytes=4 * (n_rows * heads * (f + fa) + n_seg * heads * (f + 2 * fa)),
+                            note="reads gate+value once, writes out+max+den"))
         ctx.save_for_backward(gate, value, u, seg_of_row, out, smax, sden)
         ctx.eps = eps
         return out
@@ -47,7 +50,10 @@ class _SegSoftmax(torch.autograd.Function):
         d_value = torch.empty_like(value)
         _lib.call("cgat_seg_softmax_bwd", _lib.ptr(gate), _lib.ptr(value), _lib.ptr(u), _lib.ptr(seg_of_row),
                   _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(d_out), n_rows, heads, f, fa,
-                  ctx.eps, _lib.ptr(d_gate), _lib.ptr(d_value), _lib.stream())
+                  ctx.eps, _lib.ptr(d_gate), _lib.ptr(d_value), _lib.stream(),
+                  work=dict(key="seg_softmax_bwd", bound="hbm",
+                            bytes=4 * (2 * n_rows * heads * (f + fa) + out.shape[0] * heads * (2 * f + 2 * fa)),
+                            note="reads gate+value, writes d_gate+d_value, per-segment stats once"))
         d_u = None
         if u is not None and ctx.needs_input_grad[2]:
             # alpha ∝ exp(gate + log u)  =>  dL/du = (dL/dgate summed over heads/channels) / u

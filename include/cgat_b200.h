@@ -68,6 +68,15 @@ int cgat_seg_softmax_bwd(const float* gate, const float* value, const float* u, 
                          int64_t n_rows, int32_t heads, int32_t f, int32_t fa, float eps,
                          float* d_gate, float* d_value, void* stream);
 
+/* ---- dense contraction on the tensor cores -----------
+ * C[M,N] = act(A[M,K] * B[N,K]^T + bias[N]); fp32 in/out; tcgen05 kind::tf32 with hi/lo error
+ * compensation (3 passes) so results stay at fp32 accuracy.  Replaces the cuDNN grouped-conv /
+ * cuBLAS sgemm calls the reference dispatches from nn.Conv1d / nn.Linear (reference
+ * CGAT/CGAT.py:91-109, CGAT/Hypernetworksmp.py:82-83, CGAT/message_changed.py:58-63).
+ * act: 0 none, 1 LeakyReLU(0.01), 2 tanh, 3 ReLU.  K, lda, ldb multiples of 4; A, B 16-B aligned. */
+int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
+                   int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

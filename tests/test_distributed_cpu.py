@@ -1,0 +1,53 @@
+"""world_size-2 gloo test (CPU) of the gradient exchange used for multi-GPU training."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from cgat_b200 import distributed as cdist
+
+
+class _Toy(torch.nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.graphs = torch.nn.ModuleList([torch.nn.ModuleDict({
+            "Node": torch.nn.Linear(4, 4),
+            "Edge": torch.nn.ModuleDict({"MH_A": torch.nn.Linear(2, 2), "Pooling_NN": torch.nn.Linear(3, 3)})})
+            for _ in range(2)])
+        self.out = torch.nn.Linear(4, 1)
+
+
+def _worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)
+    model = _Toy()
+    sync = cdist.GradSync(model, world)
+    x = torch.full((3, 4), float(rank + 1))
+    loss = model.out(model.graphs[0]["Node"](x)).sum() + model.graphs[0]["Edge"]["Pooling_NN"](torch.ones(3)).sum()
+    loss.backward()
+    local = sync.flat.clone()
+    sync.all_reduce()
+    gathered = [torch.zeros_like(local) for _ in range(world)]
+    dist.all_gather(gathered, local)
+    assert torch.allclose(sync.flat, sum(gathered) / world)
+    assert model.out.weight.grad.data_ptr() >= sync.flat.data_ptr()  # grads are views of the flat buffer
+    sync.zero_grad()
+    assert float(model.out.weight.grad.abs().sum()) == 0.0
+    dist.destroy_process_group()
+
+
+def test_grad_sync_gloo_world2():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    mp.spawn(_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_dead_parameters_excluded():
+    names = [n for n, _ in cdist.live_parameters(_Toy())]
+    assert not any(".Edge.MH_A." in n for n in names)
+    assert not any(n.startswith("graphs.1.Edge.Pooling_NN.") for n in names)
+    assert any(n.startswith("graphs.0.Edge.Pooling_NN.") for n in names)

@@ -1,0 +1,54 @@
+"""-m gpu: the tcgen05 3xTF32 GEMM (cgat_gemm3x_nt) against an fp64 product: fp32-level accuracy
+(a single TF32 pass would sit near 1e-3 relative), shapes with M/N/K tails, bias + activations."""
+import pytest
+import torch
+
+from cgat_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def gemm(a, b, bias=None, act=0):
+    M, K = a.shape
+    N = b.shape[0]
+    c = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    assert a.stride(1) == 1 and b.stride(1) == 1
+    _lib.call("cgat_gemm3x_nt", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), _lib.ptr(bias), _lib.ptr(c),
+              c.stride(0), M, N, K, act, _lib.stream())
+    return c
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 32), (128, 128, 128), (256, 256, 128), (5, 7, 4), (300, 200, 200),
+                                   (119, 5120, 128), (1000, 128, 5120), (129, 16512, 128), (64, 64, 256)])
+def test_gemm3x_matches_fp64(M, N, K):
+    g = torch.Generator().manual_seed(M * 31 + N * 7 + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    b = torch.randn(N, K, generator=g).to(DEV)
+    c = gemm(a, b)
+    ref = a.double() @ b.double().t()
+    err = (c.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    # fp32 sgemm sits around 1e-6 * sqrt(K); one TF32 pass around 5e-4
+    assert err <= 2e-6 * scale * max(1.0, (K / 128) ** 0.5) + 1e-6, f"max abs err {err:.3e} (scale {scale:.3e})"
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 3])
+def test_gemm3x_bias_activation(act):
+    g = torch.Generator().manual_seed(act)
+    a = torch.randn(200, 128, generator=g).to(DEV)
+    b = (torch.randn(384, 128, generator=g) / 11).to(DEV)
+    bias = torch.randn(384, generator=g).to(DEV)
+    c = gemm(a, b, bias, act)
+    ref = a.double() @ b.double().t() + bias.double()
+    ref = [ref, torch.nn.functional.leaky_relu(ref, 0.01), torch.tanh(ref), torch.relu(ref)][act]
+    assert (c.double() - ref).abs().max().item() < 5e-6
+
+
+def test_gemm3x_strided_operands():
+    g = torch.Generator().manual_seed(9)
+    big = torch.randn(300, 384, generator=g).to(DEV)
+    a = big[:, 128:256]                        # lda = 384, K = 128
+    b = torch.randn(64, 128, generator=g).to(DEV)
+    c = gemm(a, b)
+    assert (c.double() - a.double() @ b.double().t()).abs().max().item() < 2e-5

@@ -1,0 +1,106 @@
+"""-m gpu: the CUDA kernels, through the C ABI, against the CPU oracle on the same seeded inputs."""
+import numpy as np
+import pytest
+import torch
+
+from cgat_b200 import _lib, graph, ops, synthetic
+from oracle import cgat_oracle as O
+from tests._cases import assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rand_edges(n, e, seed):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (e,), generator=g)
+    dst = torch.randint(0, n, (e,), generator=g)
+    attr = torch.randint(1, 25, (e,), generator=g)
+    return torch.stack([src, dst]), attr
+
+
+@pytest.mark.parametrize("n,e,seed", [(1, 1, 0), (7, 0, 1), (50, 600, 2), (5000, 60000, 3), (3, 5000, 4),
+                                      (100000, 1200000, 5)])
+def test_csr_build_bit_exact(n, e, seed):
+    ei, attr = _rand_edges(n, e, seed)
+    plan = graph.build_edge_plan(ei.to(DEV), attr.to(DEV), n)
+    perm, rowptr = O.csr_by_destination(ei, n)
+    assert torch.equal(plan.perm.cpu().long(), perm)
+    assert torch.equal(plan.rowptr.cpu().long(), rowptr)
+    assert torch.equal(plan.src.cpu().long(), ei[0][perm])
+    assert torch.equal(plan.dst.cpu().long(), ei[1][perm])
+    assert torch.equal(plan.rank.cpu().long(), attr[perm])
+
+
+def test_csr_build_on_synthetic_batch():
+    sb = synthetic.make_batch(500, 12, seed=1)
+    g = sb.graph
+    plan = graph.build_edge_plan(g.edge_index.to(DEV), g.edge_attr.to(DEV), g.num_nodes)
+    perm, rowptr = O.csr_by_destination(g.edge_index, g.num_nodes)
+    assert torch.equal(plan.perm.cpu().long(), perm) and torch.equal(plan.rowptr.cpu().long(), rowptr)
+
+
+@pytest.mark.parametrize("sizes", [[3, 0, 0, 5, 1], [0, 0, 4], [1], [2, 2, 2, 0]])
+def test_segment_ptr(sizes):
+    idx = torch.repeat_interleave(torch.arange(len(sizes)), torch.tensor(sizes))
+    plan = graph.build_segment_plan(idx.to(DEV), len(sizes))
+    assert torch.equal(plan.ptr.cpu().long(), O.segment_ptr(idx, len(sizes)))
+    assert torch.equal(plan.index.cpu().long(), idx)
+
+
+def _softmax_case(n_seg, heads, f, fa, with_u, seed, max_len=40):
+    g = torch.Generator().manual_seed(seed)
+    lens = torch.randint(0, max_len, (n_seg,), generator=g)
+    lens[0] = 0  # an empty segment
+    idx = torch.repeat_interleave(torch.arange(n_seg), lens)
+    n = idx.numel()
+    gate = 3 * torch.randn(n, heads, fa, generator=g)
+    val = torch.randn(n, heads, f, generator=g)
+    u = (torch.rand(n, generator=g) + 0.05) if with_u else None
+    return idx, gate, val, u
+
+
+@pytest.mark.parametrize("heads,f,fa,with_u,eps", [(5, 128, 128, False, 1e-16), (5, 128, 1, False, 1e-16),
+                                                   (1, 128, 1, True, 1e-13), (3, 20, 20, True, 1e-16),
+                                                   (8, 256, 256, False, 1e-16)])
+def test_seg_softmax_fwd_bwd(heads, f, fa, with_u, eps):
+    n_seg = 97
+    idx, gate, val, u = _softmax_case(n_seg, heads, f, fa, with_u, seed=heads * 7 + f)
+    # oracle (fp64 on CPU)
+    gd, vd = gate.double().requires_grad_(True), val.double().requires_grad_(True)
+    ud = u.double().requires_grad_(True) if with_u else None
+    e = (gd - O.seg_max(gd.detach(), idx, n_seg)[idx]).exp()
+    if with_u:
+        e = e * ud.view(-1, 1, 1)
+    alpha = e / (O.seg_sum(e, idx, n_seg)[idx] + eps)
+    ref = O.seg_sum(alpha * vd, idx, n_seg)
+    w = torch.randn(ref.shape, generator=torch.Generator().manual_seed(1)).double()
+    (ref * w).sum().backward()
+    # kernel
+    plan = graph.build_segment_plan(idx.to(DEV), n_seg)
+    gc, vc = gate.to(DEV).requires_grad_(True), val.to(DEV).requires_grad_(True)
+    uc = u.to(DEV).requires_grad_(True) if with_u else None
+    out = ops.seg_softmax(gc, vc, plan, u=uc, eps=eps)
+    (out * w.float().to(DEV)).sum().backward()
+    assert_close(out.detach(), ref.detach(), "out", atol=1e-5, rtol=1e-5)
+    assert_close(gc.grad, gd.grad, "d_gate", atol=1e-5, rtol=1e-4)
+    assert_close(vc.grad, vd.grad, "d_value", atol=1e-5, rtol=1e-4)
+    if with_u:
+        assert_close(uc.grad, ud.grad, "d_u", atol=1e-4, rtol=1e-3)
+
+
+def test_seg_softmax_deterministic_and_long_segments():
+    idx, gate, val, _ = _softmax_case(11, 5, 128, 128, False, seed=3, max_len=3000)
+    plan = graph.build_segment_plan(idx.to(DEV), 11)
+    a = ops.seg_softmax(gate.to(DEV), val.to(DEV), plan)
+    b = ops.seg_softmax(gate.to(DEV), val.to(DEV), plan)
+    assert torch.equal(a, b)
+    e = (gate.double() - O.seg_max(gate.double(), idx, 11)[idx]).exp()
+    ref = O.seg_sum(e / (O.seg_sum(e, idx, 11)[idx] + 1e-16) * val.double(), idx, 11)
+    assert_close(a, ref, "long segments", atol=1e-5, rtol=1e-5)
+
+
+def test_library_loaded_and_counting():
+    before = _lib.launch_count()
+    graph.build_segment_plan(torch.zeros(4, dtype=torch.int64, device=DEV), 1)
+    assert _lib.launch_count() > before
