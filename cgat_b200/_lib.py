@@ -29,6 +29,9 @@ SIGNATURES = {
     "cgat_seg_softmax_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F32,
                                             _P, _P, _P]),
     "cgat_gemm3x_nt": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I32, _P]),
+    "cgat_packed_floats": (_I64, [_I64, _I64]),
+    "cgat_pack_kmajor": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
+    "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
 }
 
 

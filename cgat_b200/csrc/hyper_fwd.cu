@@ -1,0 +1,230 @@
+// Fused hypernetwork linear layer, forward (kernel K5).
+//
+// Reference arithmetic (CGAT/Hypernetworksmp.py:243-254 HyperLinear.forward + :205-209 BatchLinear):
+//     p[n,:]   = Wl z[n,:] + bl                 (Linear F -> F*F+F, the last layer of FCBlock)
+//     y_out[n,o] = sum_i p[n, o*F+i] * y_in[n,i] + p[n, F*F+o]
+// As written the reference materialises p: (N, F*F+F) = 66 KB per atom per hyper-layer in HBM.
+// Here p never leaves the SM: for each output channel o the tile D_o[n,i] = sum_k z[n,k] Wl[o*F+i,k]
+// is produced by tcgen05 MMAs (3xTF32, accumulators in TMEM, atoms on the 128 TMEM lanes) and is
+// contracted against y_in[n,:] by the thread that owns lane n while the next tile is being computed
+// (two TMEM accumulator buffers).  The bias-shaped remainder
+//     e[n,o] = sum_i bl[o*F+i] y_in[n,i] + sum_k Wl[F*F+o,k] z[n,k] + bl[F*F+o]
+// is a plain (N x 2F) x (2F x F) product computed beforehand by cgat_gemm3x_nt and added here.
+//
+// Roles (288 threads, one persistent CTA per SM):
+//   warps 0-3  epilogue: y_in row in registers, tcgen05.ld + FMA row-dot, store y_out
+//   warps 4-7  stage the z tile (fp32 -> tf32 hi/lo, SWIZZLE_128B K-major); warp 4 lane 0 then streams the
+//              pre-packed weight stages with cp.async.bulk (32 KB each) through a 3-deep mbarrier ring
+//   warp  8    TMEM allocation + single-thread MMA issue
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cgat {
+namespace {
+using namespace tc;
+
+template <int F>
+struct HyperCfg {
+  static constexpr int kKC = F / kPackChunk;                    // K chunks of 32 floats
+  static constexpr int kABytes = kKC * (int)kPackStageBytes;    // z tile, hi+lo per chunk
+  static constexpr int kStages = 3;
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + 1024 + kBarBytes;
+  static constexpr int kThreads = 288;
+  static constexpr int kTmemCols = 2 * F;                       // two accumulator buffers
+};
+
+template <int F>
+__global__ void __launch_bounds__(HyperCfg<F>::kThreads, 1)
+hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
+                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
+  using Cfg = HyperCfg<F>;
+  static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_smem = smem;                                   // [kKC][hi|lo][16 KB]
+  uint8_t* b_smem = smem + Cfg::kABytes;                    // [kStages][hi|lo][16 KB]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(b_smem + Cfg::kStages * kPackStageBytes);
+  uint64_t* full = bars;                                    // [kStages] TMA -> MMA
+  uint64_t* empty = bars + Cfg::kStages;                    // [kStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;            // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;                     // [2] epilogue -> MMA
+  uint64_t* a_full = tmem_empty + 2;                        // stagers -> MMA
+  uint64_t* a_free = a_full + 1;                            // MMA -> stagers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (n_atoms + 127) / 128;
+  const int n_chunks = F / oc;
+  const int n_items = n_tiles * n_chunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    mbar_init(a_full, 128);
+    mbar_init(a_free, 1);
+    mbar_init_fence();
+  }
+  if (warp == 8) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ epilogue
+    uint32_t ocount = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
+      const int n = tile * 128 + warp * 32 + lane;
+      const bool valid = n < n_atoms;
+      float y[F];
+#pragma unroll
+      for (int j = 0; j < F / 4; ++j) {
+        float4 t = valid ? __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F) + j)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+      }
+      for (int oi = 0; oi < oc; ++oi, ++ocount) {
+        const int o = chunk * oc + oi;
+        const uint32_t b = ocount & 1u;
+        mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
+        tc_fence_after();
+        float acc = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < F / 32; ++cc) {
+          float v[32];
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * F + cc * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) acc = fmaf(v[j], y[cc * 32 + j], acc);
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[b]);
+        if (valid) y_out[(int64_t)n * F + o] = acc + __ldg(e_term + (int64_t)n * F + o);
+      }
+    }
+  } else if (warp < 8) {
+    // ------------------------------------------------------------------ z-tile stagers + weight TMA
+    const int st = tid - 128;  // 0..127
+    uint32_t it = 0, cnt = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
+      mbar_wait(a_free, (it + 1) & 1u);  // previous item's MMAs have finished reading the z tile
+#pragma unroll 1
+      for (int kc = 0; kc < Cfg::kKC; ++kc) {
+        float4 v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = st + 128 * j, r = idx >> 3, c = idx & 7;
+          const int gr = tile * 128 + r;
+          v[j] = gr < n_atoms ? __ldg(reinterpret_cast<const float4*>(z + (int64_t)gr * F + kc * 32 + c * 4))
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint8_t* hi = a_smem + kc * kPackStageBytes;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int idx = st + 128 * j;
+          const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+          float4 h, l;
+          split_tf32(v[j], h, l);
+          *reinterpret_cast<float4*>(hi + off) = h;
+          *reinterpret_cast<float4*>(hi + kPackImageBytes + off) = l;
+        }
+      }
+      fence_async_smem();
+      mbar_arrive(a_full);
+      if (st == 0) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_packed);
+        for (int oi = 0; oi < oc; ++oi) {
+          const int o = chunk * oc + oi;
+          for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
+            const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
+            mbar_wait(&empty[s], (u + 1) & 1u);
+            mbar_arrive_expect_tx(&full[s], kPackStageBytes);
+            bulk_g2s(b_smem + s * kPackStageBytes, wsrc + ((int64_t)o * Cfg::kKC + kc) * kPackStageBytes,
+                     kPackStageBytes, &full[s]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(128, F);
+    uint32_t it = 0, cnt = 0, ocount = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      mbar_wait(a_full, it & 1u);
+      tc_fence_after();
+      for (int oi = 0; oi < oc; ++oi, ++ocount) {
+        const uint32_t b = ocount & 1u;
+        mbar_wait(&tmem_empty[b], ((ocount >> 1) + 1) & 1u);
+        tc_fence_after();
+        for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
+          const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
+          mbar_wait(&full[s], u & 1u);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
+            const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes), b_lo = b_hi + kPackImageBytes;
+            const uint32_t d = tmem + b * F;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t off = ks * 32;
+              umma_tf32(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+            }
+            umma_commit(&empty[s]);
+            if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);
+          }
+          __syncwarp();
+        }
+      }
+      if (lane == 0) umma_commit(a_free);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace
+}  // namespace cgat
+
+using namespace cgat;
+
+// y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) y_in[n,i] + e_term[n,o]
+//   z, y_in, e_term, y_out: (n_atoms, F) fp32 contiguous; w_packed: cgat_pack_kmajor of W[:F*F, :F]
+extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
+                                     float* y_out, int64_t n_atoms, int32_t f, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_atoms <= 0) return 0;
+  if (f != 128) return fail(-2, "cgat_hyper_rowdot_fwd: only F = 128 is instantiated");
+  if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_rowdot_fwd: too many atoms");
+  using Cfg = HyperCfg<128>;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int n_tiles = (int)((n_atoms + 127) / 128);
+  // output channels per work item: smaller chunks when there are few atom tiles, so that all SMs get work
+  int oc = 16;
+  while (oc > 4 && (int64_t)n_tiles * (f / oc) < 3 * kNumSMs) oc >>= 1;
+  const int n_items = n_tiles * (f / oc);
+  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  hyper_rowdot_fwd_kernel<128><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(z, y_in, e_term, w_packed, y_out,
+                                                                                  (int)n_atoms, oc);
+  return check_launch("hyper_rowdot_fwd_kernel");
+}

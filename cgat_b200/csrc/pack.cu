@@ -1,0 +1,50 @@
+// Weight packing for the tensor-core kernels: fp32 row-major [rows x k] -> tiles of 128 rows x 32
+// floats, pre-split into (tf32 hi, tf32 lo) and pre-swizzled (canonical K-major SWIZZLE_128B), so the
+// consuming kernel fetches a ready UMMA operand stage with ONE bulk async copy and spends no
+// instructions on conversion.  Runs once per optimizer step (training) or once per model (inference).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cgat {
+namespace {
+using namespace tc;
+
+// grid: (k_chunks, row_tiles); 256 threads: thread -> (row r = idx/8, 16-byte chunk c = idx%8)
+__global__ void pack_kmajor_kernel(const float* __restrict__ w, int64_t ld, int rows, int k, int transpose,
+                                   float* __restrict__ out) {
+  const int kc = blockIdx.x, rt = blockIdx.y;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + ((int64_t)rt * gridDim.x + kc) * kPackStageBytes;
+  for (int idx = threadIdx.x; idx < kPackRows * 8; idx += blockDim.x) {
+    const int r = idx >> 3, c = idx & 7;
+    const int gr = rt * kPackRows + r, gk = kc * kPackChunk + c * 4;
+    float v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float x = 0.f;
+      if (gr < rows && gk + j < k) x = transpose ? w[(int64_t)(gk + j) * ld + gr] : w[(int64_t)gr * ld + gk + j];
+      v[j] = x;
+    }
+    float4 hi, lo;
+    split_tf32(make_float4(v[0], v[1], v[2], v[3]), hi, lo);
+    const uint32_t off = sw128_offset(r, c);
+    *reinterpret_cast<float4*>(dst + off) = hi;
+    *reinterpret_cast<float4*>(dst + kPackImageBytes + off) = lo;
+  }
+}
+
+}  // namespace
+}  // namespace cgat
+
+using namespace cgat;
+
+extern "C" int64_t cgat_packed_floats(int64_t rows, int64_t k) { return tc::packed_floats(rows, k); }
+
+// w: [rows x k] (transpose=0, leading dimension ld) or its transpose stored as [k x rows] (transpose=1).
+extern "C" int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
+                                void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows <= 0 || k <= 0) return 0;
+  dim3 grid((unsigned)ceil_div(k, tc::kPackChunk), (unsigned)ceil_div(rows, tc::kPackRows));
+  pack_kmajor_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, out);
+  return check_launch("pack_kmajor_kernel");
+}

@@ -126,17 +126,58 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ---- fp32 -> tf32 hi/lo split -------------------------------------------------------------------
-// hi keeps the top 19 bits (exactly representable in TF32 whatever the hardware's conversion mode),
-// lo = x - hi is exact in fp32 and is itself fed as TF32: a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo.
+// hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi) (the subtraction is exact in
+// fp32).  Both are exactly representable in TF32, so the tensor core's own operand conversion
+// (truncation) is lossless and the residual is unbiased: a*b ~= a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with
+// a relative error of ~2^-22 per product (the dropped lo*lo term is ~2^-24).
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
-  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
-  lo = x - hi;
+  hi = round_tf32(x);
+  lo = round_tf32(x - hi);
 }
 __device__ __forceinline__ void split_tf32(const float4& x, float4& hi, float4& lo) {
   split_tf32(x.x, hi.x, lo.x);
   split_tf32(x.y, hi.y, lo.y);
   split_tf32(x.z, hi.z, lo.z);
   split_tf32(x.w, hi.w, lo.w);
+}
+
+}  // namespace tc
+}  // namespace cgat
+
+// ---- bulk async copy (TMA engine, no tensor map: contiguous pre-packed operand tiles) -----------
+namespace cgat {
+namespace tc {
+
+// this thread arrives on `bar` and announces `bytes` of async-copy traffic that must also land
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+// global -> shared, completion signalled on `bar` (SASS: UBLKCP).  16-byte aligned, size % 16 == 0.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// Packed K-major operand: a [rows x k] fp32 matrix cut into tiles of kPackRows rows x 32 floats, each
+// stored as two consecutive 16 KB SWIZZLE_128B images (tf32 hi, then tf32 lo) in the order
+// [row_tile][k_chunk][hi|lo].  One bulk copy of 32 KB brings a ready-to-multiply stage.
+constexpr int kPackRows = 128;
+constexpr int kPackChunk = 32;
+constexpr uint32_t kPackImageBytes = kPackRows * kPackChunk * 4;  // 16 KB
+constexpr uint32_t kPackStageBytes = 2 * kPackImageBytes;         // hi + lo
+
+__host__ __device__ inline int64_t packed_floats(int64_t rows, int64_t k) {
+  int64_t rt = (rows + kPackRows - 1) / kPackRows, kc = (k + kPackChunk - 1) / kPackChunk;
+  return rt * kc * (kPackStageBytes / 4);
 }
 
 }  // namespace tc

@@ -112,10 +112,90 @@ def edge_attention(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, 
     return agg.mean(dim=1)
 
 
+# ----------------------------------------------------------------------------------------------
+# Tensor-core pieces (tcgen05, 3xTF32 error-compensated; fp32 in / fp32 out)
+# ----------------------------------------------------------------------------------------------
+def gemm3x(a, w, bias=None, act=0, out=None):
+    """act(a @ w.T + bias) on the tensor cores (cgat_gemm3x_nt). a (M,K), w (N,K): rows contiguous."""
+    M, K = a.shape
+    N = w.shape[0]
+    if a.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("gemm3x needs row-contiguous operands")
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if not a.is_cuda:
+        raise _lib.CgatLibraryError("cgat_b200 kernels need CUDA tensors (there is no CPU path)")
+    _lib.call("cgat_gemm3x_nt", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _lib.ptr(bias),
+              out.data_ptr(), out.stride(0), M, N, K, act, _lib.stream(),
+              work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))
+    return out
+
+
+def packed_kmajor(w, rows=None, transpose=False):
+    """Pre-split / pre-swizzled copy of w[:rows] (2-D view of a contiguous weight) for the fused
+    kernels.  Cached ON the tensor object and keyed by its autograd version counter, so an in-place
+    optimizer update (which bumps `_version`) triggers a repack and a freed tensor cannot leave a
+    stale entry behind."""
+    w2 = w.detach().view(w.shape[0], -1)
+    rows = w2.shape[0] if rows is None else rows
+    cache = w.__dict__.setdefault("_cgat_packed", {})
+    key = (rows, transpose)
+    hit = cache.get(key)
+    if hit is not None and hit[0] == w._version and hit[2] == w.data_ptr():
+        return hit[1]
+    lib = _lib.load()
+    n_rows, k = (w2.shape[1], rows) if transpose else (rows, w2.shape[1])
+    buf = hit[1] if hit is not None else torch.empty(int(lib.cgat_packed_floats(n_rows, k)), dtype=torch.float32,
+                                                     device=w.device)
+    _lib.call("cgat_pack_kmajor", _lib.ptr(w2), w2.stride(0), n_rows, k, int(transpose), _lib.ptr(buf),
+              _lib.stream(), work=dict(key="pack_kmajor", bound="hbm", bytes=12.0 * n_rows * k))
+    cache[key] = (w._version, buf, w.data_ptr())
+    return buf
+
+
+class _HyperLinear(torch.autograd.Function):
+    """y_out[n] = reshape(W z[n] + b)[:F*F] y[n] + (W z[n] + b)[F*F:]   (reference HyperLinear.forward +
+    BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209) with the (N, F*F+F) predicted-weight
+    tensor never materialised in forward (cgat_hyper_rowdot_fwd)."""
+
+    @staticmethod
+    def forward(ctx, z, weight, bias, y, w_packed):
+        z, y = _f32c(z), _f32c(y)
+        n, f = y.shape
+        ff = f * f
+        # bias-shaped remainder: e = [y | z] @ [bl.view(F,F) | W[F*F:]]^T + bl[F*F:]
+        we = torch.cat([bias[:ff].view(f, f), weight[ff:]], dim=1)
+        e = gemm3x(torch.cat([y, z], dim=1), we, bias[ff:].contiguous())
+        out = torch.empty_like(y)
+        _lib.call("cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y), _lib.ptr(e), _lib.ptr(w_packed),
+                  _lib.ptr(out), n, f, _lib.stream(),
+                  work=dict(key="hyper_rowdot_fwd", bound="tensor", flops=2.0 * n * f * ff,
+                            note="3xTF32: 3 tensor passes per algorithmic flop"))
+        ctx.save_for_backward(z, weight, bias, y)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        # recompute the predicted weights (library GEMM path for now; fused backward kernels replace this)
+        z, weight, bias, y = ctx.saved_tensors
+        n, f = y.shape
+        ff = f * f
+        g = g.contiguous()
+        p_w = torch.addmm(bias[:ff], z, weight[:ff].t()).view(n, f, f)          # (N, out, in)
+        g_y = torch.bmm(g.unsqueeze(1), p_w).squeeze(1)
+        g_p = torch.cat([(g.unsqueeze(2) * y.unsqueeze(1)).reshape(n, ff), g], dim=1)
+        g_z = g_p @ weight
+        g_w = g_p.t() @ z
+        g_b = g_p.sum(dim=0)
+        return g_z, g_w, g_b, g_y, None
+
+
 def hyper_linear(z, weight, bias, y, out_ch):
     """y_out[n] = reshape(weight z[n] + bias)[:out*in] y[n] + (...)[out*in:]
     (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209)."""
     in_ch = y.shape[1]
+    if in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
+        return _HyperLinear.apply(z, weight, bias, y, packed_kmajor(weight, in_ch * out_ch))
     p = torch.addmm(bias, z, weight.t())                            # (N, out*in + out)
     w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
     b = p[:, in_ch * out_ch:]

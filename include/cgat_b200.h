@@ -77,6 +77,22 @@ int cgat_seg_softmax_bwd(const float* gate, const float* value, const float* u, 
 int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act, void* stream);
 
+/* ---- packed tensor-core operands ---------------------------------------------------------------
+ * fp32 [rows x k] (or its transpose, transpose=1: stored [k x rows]) -> 128-row x 32-float tiles,
+ * pre-split into (tf32 hi, tf32 lo) and pre-swizzled; layout [row_tile][k_chunk][hi|lo][16 KB].
+ * `out` holds cgat_packed_floats(rows,k) floats.  Repack after every weight update.              */
+int64_t cgat_packed_floats(int64_t rows, int64_t k);
+int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
+                     void* stream);
+
+/* ---- fused hypernetwork linear layer ----------------------------------
+ * y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) * y_in[n,i] + e_term[n,o]
+ * Replaces Linear(F -> F*F+F) + view + BatchLinear (reference CGAT/Hypernetworksmp.py:243-254,
+ * 205-209) without materialising the (N, F*F+F) predicted-weight tensor.  w_packed =
+ * cgat_pack_kmajor(W[:F*F,:F]); e_term carries the bias-shaped remainder (see hyper_fwd.cu).   */
+int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
+                          float* y_out, int64_t n_atoms, int32_t f, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,10 +27,13 @@ def test_gemm3x_matches_fp64(M, N, K):
     b = torch.randn(N, K, generator=g).to(DEV)
     c = gemm(a, b)
     ref = a.double() @ b.double().t()
-    err = (c.double() - ref).abs().max().item()
-    scale = ref.abs().max().item()
-    # fp32 sgemm sits around 1e-6 * sqrt(K); one TF32 pass around 5e-4
-    assert err <= 2e-6 * scale * max(1.0, (K / 128) ** 0.5) + 1e-6, f"max abs err {err:.3e} (scale {scale:.3e})"
+    bound = a.double().abs() @ b.double().abs().t()        # sum_k |a||b|: the natural error scale
+    rel = ((c.double() - ref).abs() / bound).max().item()
+    print(f"gemm3x {M}x{N}x{K}: max err / sum|a||b| = {rel:.3e}")
+    # each of the 3K/8 accumulating MMAs rounds the fp32 accumulator once (~1e-7 relative, random
+    # walk), like an fp32 FMA chain of that length; a single TF32 pass would sit near 3e-4
+    limit = 3e-7 + 2e-7 * (3 * K / 8) ** 0.5
+    assert rel <= limit, f"max err / sum|a||b| = {rel:.3e} (limit {limit:.3e})"
 
 
 @pytest.mark.parametrize("act", [0, 1, 2, 3])
@@ -42,7 +45,7 @@ def test_gemm3x_bias_activation(act):
     c = gemm(a, b, bias, act)
     ref = a.double() @ b.double().t() + bias.double()
     ref = [ref, torch.nn.functional.leaky_relu(ref, 0.01), torch.tanh(ref), torch.relu(ref)][act]
-    assert (c.double() - ref).abs().max().item() < 5e-6
+    assert (c.double() - ref).abs().max().item() < 2e-5
 
 
 def test_gemm3x_strided_operands():
@@ -51,4 +54,5 @@ def test_gemm3x_strided_operands():
     a = big[:, 128:256]                        # lda = 384, K = 128
     b = torch.randn(64, 128, generator=g).to(DEV)
     c = gemm(a, b)
-    assert (c.double() - a.double() @ b.double().t()).abs().max().item() < 2e-5
+    bound = a.double().abs() @ b.double().abs().t()
+    assert ((c.double() - a.double() @ b.double().t()).abs() / bound).max().item() < 2e-6

@@ -104,3 +104,44 @@ def test_library_loaded_and_counting():
     before = _lib.launch_count()
     graph.build_segment_plan(torch.zeros(4, dtype=torch.int64, device=DEV), 1)
     assert _lib.launch_count() > before
+
+
+@pytest.mark.parametrize("n", [1, 119, 128, 700, 5559])
+def test_hyper_linear_fused_fwd_bwd(n):
+    """cgat_hyper_rowdot_fwd (+ e-term GEMM) against the reference arithmetic in fp64
+    (HyperLinear.forward + BatchLinear.forward, reference CGAT/Hypernetworksmp.py:243-254, 205-209)."""
+    f = 128
+    g = torch.Generator().manual_seed(n)
+    z = torch.tanh(torch.randn(n, f, generator=g))
+    y = torch.randn(n, f, generator=g)
+    w = torch.randn(f * f + f, f, generator=g) * 0.0125
+    b = torch.randn(f * f + f, generator=g) * 0.09
+    zd, yd, wd, bd = (t.double().requires_grad_(True) for t in (z, y, w, b))
+    p = zd @ wd.t() + bd
+    ref = torch.einsum("noi,ni->no", p[:, : f * f].view(n, f, f), yd) + p[:, f * f:]
+    gw = torch.randn(n, f, generator=g).double()
+    (ref * gw).sum().backward()
+    zc, yc, wc, bc = (t.to(DEV).requires_grad_(True) for t in (z, y, w, b))
+    out = ops.hyper_linear(zc, wc, bc, yc, f)
+    (out * gw.float().to(DEV)).sum().backward()
+    assert_close(out.detach(), ref.detach(), "hyper fwd", atol=2e-5, rtol=1e-4)
+    assert_close(zc.grad, zd.grad, "g_z", atol=1e-4, rtol=1e-3)
+    assert_close(yc.grad, yd.grad, "g_y", atol=1e-4, rtol=1e-3)
+    assert_close(wc.grad, wd.grad, "g_w", atol=1e-4, rtol=1e-3)
+    assert_close(bc.grad, bd.grad, "g_b", atol=1e-4, rtol=1e-3)
+
+
+def test_pack_repack_on_weight_update():
+    f = 128
+    w = torch.randn(f * f + f, f, device=DEV) * 0.01
+    p1 = ops.packed_kmajor(w, f * f).clone()
+    assert ops.packed_kmajor(w, f * f).data_ptr() == ops.packed_kmajor(w, f * f).data_ptr()
+    w.add_(1.0)
+    p2 = ops.packed_kmajor(w, f * f)
+    assert not torch.equal(p1, p2)
+    # a different tensor that lands on the same address must not see the old packing
+    ptr = w.data_ptr()
+    del w, p2
+    w2 = torch.randn(f * f + f, f, device=DEV) * 0.01
+    p3 = ops.packed_kmajor(w2, f * f)
+    assert w2.data_ptr() != ptr or not torch.equal(p1, p3)
