@@ -129,10 +129,7 @@ class GATConvNodes(nn.Module):
     def aggregate(self, x, edge_table, plan: EdgePlan):
         """(N, F): mean over heads of the attention-weighted messages arriving at each atom
         (reference message() + scatter-add + update()'s head-mean, CGAT.py:319-329)."""
-        a, m = self.MH_A, self.MH_M
-        return ops.edge_attention(x, edge_table, plan,
-                                  a.w_in(), a.fc_in.bias, a.w_out(), a.fc_out.bias,
-                                  m.w_in(), m.fc_in.bias, m.w_out(), m.fc_out.bias, self.heads)
+        return ops.edge_attention(x, edge_table, plan, self.MH_A, self.MH_M, self.heads)
 
     def forward(self, x, edge_table, plan: EdgePlan, x_0):
         aggr = self.aggregate(x, edge_table, plan)

@@ -32,6 +32,8 @@ SIGNATURES = {
     "cgat_packed_floats": (_I64, [_I64, _I64]),
     "cgat_pack_kmajor": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
     "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_edge_attn_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
+                                          _I32, _I32, _F32, _P]),
 }
 
 

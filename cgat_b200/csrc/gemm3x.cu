@@ -96,7 +96,9 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
     mbar_init(accum, 1);
     mbar_init_fence();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, BN);
+  // columns [0,BN): hi*hi sum; [BN,2BN): the 2^-11-sized correction terms, kept apart so the large
+  // accumulator is truncated K/8 times instead of 3K/8 (the tensor core truncates on every MMA)
+  if (warp == 4) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -120,8 +122,9 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
-      float v[32];
+      float v[32], w[32];
       tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + BN + cc * 32, w);
       tmem_ld_wait();
       const int nb = n0 + cc * 32;
       if (m < M) {
@@ -129,7 +132,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
         for (int j = 0; j < 32; ++j) {
           int n = nb + j;
           float b = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
-          v[j] = apply_act(v[j] + b, act);
+          v[j] = apply_act((v[j] + w[j]) + b, act);
         }
         float* crow = C + (int64_t)m * ldc + nb;
         if (vec_ok && nb + 32 <= N) {
@@ -159,9 +162,9 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
         for (int ks = 0; ks < kKC / 8; ++ks) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
           const uint32_t o = ks * 32;
-          umma_tf32(tmem, umma_desc_k_sw128(a_lo + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
-          umma_tf32(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_lo + o), idesc, 1);
-          umma_tf32(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_hi + o), idesc, 1);
+          umma_tf32(tmem + BN, umma_desc_k_sw128(a_lo + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
+          umma_tf32(tmem + BN, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_lo + o), idesc, 1);
+          umma_tf32(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
         }
         umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
         if (kc == nk - 1) umma_commit(accum);
@@ -172,7 +175,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem, BN);
+    tmem_dealloc(tmem, 2 * BN);
   }
 }
 

@@ -31,7 +31,10 @@ struct HyperCfg {
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + 1024 + kBarBytes;
   static constexpr int kThreads = 288;
-  static constexpr int kTmemCols = 2 * F;                       // two accumulator buffers
+  // two buffers x (main, correction) accumulators.  The tensor core truncates the fp32 accumulator on
+  // every MMA; keeping the 2^-11-sized lo*hi / hi*lo terms in their own accumulator means the large
+  // hi*hi sum sees K/8 truncations instead of 3K/8, and the two are added once, rounded to nearest.
+  static constexpr int kTmemCols = 4 * F;
 };
 
 template <int F>
@@ -99,11 +102,12 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
         float acc = 0.f;
 #pragma unroll
         for (int cc = 0; cc < F / 32; ++cc) {
-          float v[32];
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * F + cc * 32, v);
+          float v[32], w[32];
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + cc * 32, v);
+          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + F + cc * 32, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc = fmaf(v[j], y[cc * 32 + j], acc);
+          for (int j = 0; j < 32; ++j) acc = fmaf(v[j] + w[j], y[cc * 32 + j], acc);
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[b]);
@@ -173,13 +177,13 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
           if (lane == 0) {
             const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
             const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes), b_lo = b_hi + kPackImageBytes;
-            const uint32_t d = tmem + b * F;
+            const uint32_t d = tmem + b * 2 * F, dc = d + F;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
-              umma_tf32(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
             }
             umma_commit(&empty[s]);
             if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);

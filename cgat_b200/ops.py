@@ -3,6 +3,8 @@ allocates outputs, calls one or more kernels on the current stream, and wires th
 backward kernels into autograd.  No CPU path."""
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import _lib
@@ -74,6 +76,8 @@ def seg_softmax(gate, value, plan: SegmentPlan | None = None, *, ptr=None, seg_o
 # the hand-written segment kernels in between.  The fused sm_100a kernels replace these one by one.
 # ----------------------------------------------------------------------------------------------
 LEAKY_SLOPE = 0.01
+# numerics A/B switch for development (1 = fused tensor-core kernels; 0 = library GEMMs + segment kernels)
+_FUSED = os.environ.get("CGAT_B200_FUSED", "1") != "0"
 
 
 def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
@@ -87,8 +91,10 @@ def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
     return out.transpose(0, 1)                                                                # (n, H, Out)
 
 
-def edge_attention(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
-    """Node-attention aggregation, reference CGAT/CGAT.py:319-329 (Appendix A of SURVEY.md).
+def edge_attention_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
+    """Node-attention aggregation, reference CGAT/CGAT.py:319-329 (Appendix A of SURVEY.md) — library GEMMs +
+    the segmented-softmax kernel.  Used for the shapes the fused kernel is not instantiated for and as
+    the recompute path of its backward.
 
     m_t = [x[dst]; e(rank_t); x[src]]; the first MLP layer is linear in m_t, so it is evaluated per
     atom and per rank and only summed per edge:  W1 m_t = (x W1_i^T)[dst] + (e W1_e^T + b1)[rank] + (x W1_j^T)[src].
@@ -194,9 +200,98 @@ def hyper_linear(z, weight, bias, y, out_ch):
     """y_out[n] = reshape(weight z[n] + bias)[:out*in] y[n] + (...)[out*in:]
     (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209)."""
     in_ch = y.shape[1]
-    if in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
+    if _FUSED and z.is_cuda and in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
         return _HyperLinear.apply(z, weight, bias, y, packed_kmajor(weight, in_ch * out_ch))
     p = torch.addmm(bias, z, weight.t())                            # (N, out*in + out)
     w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
     b = p[:, in_ch * out_ch:]
     return torch.baddbmm(b.unsqueeze(2), w, y.unsqueeze(2)).squeeze(2)
+
+
+class _EdgeAttentionFused(torch.autograd.Function):
+    """Forward: per-atom / per-rank first-layer projections (cgat_gemm3x_nt) + the fused gather /
+    second-layer MMA / segmented-softmax kernel (cgat_edge_attn_fwd).  No per-edge tensor is written.
+    Backward (for now): recompute through the unfused formulation under autograd."""
+
+    @staticmethod
+    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads,
+                keep_stats):
+        x, edge_table = _f32c(x), _f32c(edge_table)
+        n, f = x.shape
+        fe = edge_table.shape[1]
+        hhd = w1a.shape[0]
+        hd = hhd // heads
+        w1a2, w1m2 = w1a.view(hhd, -1), w1m.view(hhd, -1)
+        w_atom = torch.cat([w1a2[:, :f], w1m2[:, :f], w1a2[:, f + fe:], w1m2[:, f + fe:]], dim=0)   # (4*HHd, F)
+        w_rank = torch.cat([w1a2[:, f:f + fe], w1m2[:, f:f + fe]], dim=0)                           # (2*HHd, Fe)
+        P = gemm3x(x, w_atom)                                                                        # (N, 4*HHd)
+        T = gemm3x(edge_table, w_rank, torch.cat([b1a, b1m]))                                        # (K+1, 2*HHd)
+        out = torch.empty((n, heads, f), dtype=torch.float32, device=x.device)
+        smax = torch.empty_like(out) if keep_stats else None
+        sden = torch.empty_like(out) if keep_stats else None
+        e = plan.n_edges
+        _lib.call("cgat_edge_attn_fwd", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
+                  _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed),
+                  _lib.ptr(b2a.contiguous()), _lib.ptr(b2m.contiguous()), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden),
+                  n, e, heads, f, hd, 1e-16, _lib.stream(),
+                  work=dict(key="edge_attn_fwd", bound="tensor", flops=2.0 * e * heads * hd * 2 * f,
+                            bytes=4.0 * (e * (3 + 2 * 2 * hhd) + n * heads * f),
+                            note="second MLP layer (E x Hd x F per head, gate+message) on tcgen05, 3xTF32"))
+        ctx.save_for_backward(x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m)
+        ctx.plan, ctx.heads = plan, heads
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        need = ctx.needs_input_grad[:10]
+        with torch.enable_grad():
+            ins = [t.detach().requires_grad_(nd) for t, nd in zip(saved, need)]
+            x, tab, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m = ins
+            hhd = w1a.shape[0]
+            heads = ctx.heads
+            agg = edge_attention_heads_unfused(x, tab, ctx.plan, w1a.view(hhd, -1), b1a,
+                                               w2a.view(heads, -1, hhd // heads), b2a, w1m.view(hhd, -1), b1m,
+                                               w2m.view(heads, -1, hhd // heads), b2m, heads)
+            req = [t for t, nd in zip(ins, need) if nd]
+            grads = torch.autograd.grad(agg, req, g)
+        it = iter(grads)
+        return tuple(next(it) if nd else None for nd in need) + (None,) * 5
+
+
+def edge_attention_heads_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
+    """(N, H, F) per-head aggregation through the unfused formulation (see edge_attention_unfused)."""
+    n, f = x.shape
+    fe = edge_table.shape[1]
+    hhd = w1a.shape[0]
+    hd = hhd // heads
+    w1 = torch.cat([w1a, w1m], dim=0)
+    p_dst = x @ w1[:, :f].t()
+    p_src = x @ w1[:, f + fe:].t()
+    t_rank = torch.addmm(torch.cat([b1a, b1m]), edge_table, w1[:, f:f + fe].t())
+    pre = p_dst.index_select(0, plan.dst) + p_src.index_select(0, plan.src) + t_rank.index_select(0, plan.rank)
+    hid = torch.nn.functional.leaky_relu(pre, LEAKY_SLOPE)
+    e = hid.shape[0]
+    hid_a = hid[:, :hhd].view(e, heads, hd).transpose(0, 1)
+    hid_m = hid[:, hhd:].view(e, heads, hd).transpose(0, 1)
+    gate = torch.baddbmm(b2a.view(heads, 1, -1), hid_a, w2a.transpose(1, 2)).transpose(0, 1).contiguous()
+    msg = torch.baddbmm(b2m.view(heads, 1, -1), hid_m, w2m.transpose(1, 2)).transpose(0, 1).contiguous()
+    return seg_softmax(gate, msg, ptr=plan.rowptr, seg_of_row=plan.dst, n_seg=n, eps=1e-16)
+
+
+def edge_attention(x, edge_table, plan, mh_a, mh_m, heads):
+    """(N, F): mean over heads of the attention-weighted messages arriving at each atom (reference
+    GATConvNodes.message + aggregate + the head-mean of update, CGAT/CGAT.py:319-329).  `mh_a`, `mh_m` are
+    the gate / message MultiHeadNetwork modules (parameters fc_in/fc_out in the reference's Conv1d layout)."""
+    f = x.shape[1]
+    hd = mh_a.hidden_dim
+    fused_ok = (_FUSED and x.is_cuda and f == 128 and mh_a.output_dim == f and mh_m.output_dim == f and hd % 4 == 0
+                and heads <= 8 and edge_table.shape[1] % 4 == 0)
+    if fused_ok:
+        out = _EdgeAttentionFused.apply(x, edge_table, mh_a.fc_in.weight, mh_a.fc_in.bias, mh_a.fc_out.weight,
+                                        mh_a.fc_out.bias, mh_m.fc_in.weight, mh_m.fc_in.bias, mh_m.fc_out.weight,
+                                        mh_m.fc_out.bias, packed_kmajor(mh_a.fc_out.weight),
+                                        packed_kmajor(mh_m.fc_out.weight), plan, heads, False)
+        return out.mean(dim=1)
+    return edge_attention_unfused(x, edge_table, plan, mh_a.w_in(), mh_a.fc_in.bias, mh_a.w_out(), mh_a.fc_out.bias,
+                                  mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads)

@@ -93,6 +93,21 @@ int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_
 int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
                           float* y_out, int64_t n_atoms, int32_t f, void* stream);
 
+/* ---- fused edge attention, forward ---------------------------------
+ * out[d,h,:] = sum_{t in in(d)} softmax_t(a_t,h)[:] * v_t,h[:] with
+ *   hid_t = leaky_relu(P[dst_t, dst-block] + P[src_t, src-block] + T[rank_t]),
+ *   a_t,h = W2A_h hidA_t,h + b2A_h,  v_t,h = W2M_h hidM_t,h + b2M_h.
+ * Replaces index_select/cat, the grouped Conv1d MLPs, torch_geometric softmax and scatter_add of
+ * GATConvNodes.message/aggregate (reference CGAT/CGAT.py:103-109, 319-326) in one kernel.
+ *   P (N, 4*H*Hd) = x [W1A_i; W1M_i; W1A_j; W1M_j]^T,  T (K+1, 2*H*Hd) = e [W1A_e; W1M_e]^T + [b1A; b1M]
+ *   rowptr/src/dst/rank: cgat_csr_build outputs;  w2a/w2m_packed: cgat_pack_kmajor of (H*F, Hd)
+ *   out, seg_max, seg_den: (N, H, F); seg_max/seg_den may be NULL (inference).  F = 128.          */
+int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                       const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                       const float* w2m_packed, const float* b2a, const float* b2m, float* out,
+                       float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                       int32_t f, int32_t hd, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -127,8 +127,9 @@ def test_hyper_linear_fused_fwd_bwd(n):
     assert_close(out.detach(), ref.detach(), "hyper fwd", atol=2e-5, rtol=1e-4)
     assert_close(zc.grad, zd.grad, "g_z", atol=1e-4, rtol=1e-3)
     assert_close(yc.grad, yd.grad, "g_y", atol=1e-4, rtol=1e-3)
-    assert_close(wc.grad, wd.grad, "g_w", atol=1e-4, rtol=1e-3)
-    assert_close(bc.grad, bd.grad, "g_b", atol=1e-4, rtol=1e-3)
+    # sums over all n atoms of O(1) terms: the noise floor scales with the magnitude of the sums
+    assert_close(wc.grad, wd.grad, "g_w", atol=1e-5 * wd.grad.abs().max().item() + 1e-4, rtol=1e-3)
+    assert_close(bc.grad, bd.grad, "g_b", atol=1e-5 * bd.grad.abs().max().item() + 1e-4, rtol=1e-3)
 
 
 def test_pack_repack_on_weight_update():
@@ -145,3 +146,47 @@ def test_pack_repack_on_weight_update():
     w2 = torch.randn(f * f + f, f, device=DEV) * 0.01
     p3 = ops.packed_kmajor(w2, f * f)
     assert w2.data_ptr() != ptr or not torch.equal(p1, p3)
+
+
+@pytest.mark.parametrize("n_cry,k,heads,lo,hi", [(3, 12, 5, 2, 20), (40, 12, 5, 2, 20), (2, 24, 2, 200, 256),
+                                                 (700, 12, 5, 2, 20), (1, 4, 1, 2, 3)])
+def test_edge_attention_fused_matches_oracle(n_cry, k, heads, lo, hi):
+    """cgat_edge_attn_fwd (+ projection GEMMs) against the reference arithmetic of
+    GATConvNodes.message/aggregate (reference CGAT/CGAT.py:319-329) restated in fp64."""
+    from cgat_b200.CGAT import MultiHeadNetwork
+    f, fe = 128, 128
+    sb = synthetic.make_batch(n_cry, k, seed=n_cry, atoms_lo=lo, atoms_hi=hi)
+    gidx = sb.graph
+    n = gidx.num_nodes
+    torch.manual_seed(n_cry)
+    width = 2 * f + fe
+    mh_a = MultiHeadNetwork(width, f, int(width / 1.5), heads)
+    mh_m = MultiHeadNetwork(width, f, int(width / 1.5), heads)
+    x = torch.randn(n, f) * 0.5
+    tab = torch.randn(k + 1, fe)
+    # fp64 oracle
+    sd = {}
+    for pre, mod in (("A.", mh_a), ("M.", mh_m)):
+        for kk, v in mod.state_dict().items():
+            sd[pre + kk] = v.double()
+    src, dst = gidx.edge_index
+    m = torch.cat([x.double()[dst], tab.double()[gidx.edge_attr], x.double()[src]], dim=1)
+    alpha = O.pyg_softmax(O.multi_head_network(sd, "A.", m, heads), dst, n)
+    ref = O.seg_sum(O.multi_head_network(sd, "M.", m, heads) * alpha, dst, n).mean(dim=1)
+    # fused path
+    plan = graph.build_edge_plan(gidx.edge_index.to(DEV), gidx.edge_attr.to(DEV), n)
+    mh_a, mh_m = mh_a.to(DEV), mh_m.to(DEV)
+    xc = x.to(DEV).requires_grad_(True)
+    out = ops.edge_attention(xc, tab.to(DEV), plan, mh_a, mh_m, heads)
+    assert_close(out.detach(), ref, "edge attention fwd", atol=2e-5, rtol=1e-4)
+    out2 = ops.edge_attention(xc, tab.to(DEV), plan, mh_a, mh_m, heads)
+    assert torch.equal(out, out2), "fused edge attention is not deterministic"
+    # backward runs (recompute path) and matches the oracle's gradient w.r.t. x
+    xd = x.double().requires_grad_(True)
+    m = torch.cat([xd[dst], tab.double()[gidx.edge_attr], xd[src]], dim=1)
+    alpha = O.pyg_softmax(O.multi_head_network(sd, "A.", m, heads), dst, n)
+    refg = O.seg_sum(O.multi_head_network(sd, "M.", m, heads) * alpha, dst, n).mean(dim=1)
+    w = torch.randn(n, f, generator=torch.Generator().manual_seed(5)).double()
+    (refg * w).sum().backward()
+    (out * w.float().to(DEV)).sum().backward()
+    assert_close(xc.grad, xd.grad, "edge attention d_x", atol=1e-4, rtol=1e-3)
