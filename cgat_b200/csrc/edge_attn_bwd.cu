@@ -1,0 +1,491 @@
+// Fused edge-attention backward, steps 2 and 3 (SURVEY.md §8a row A12 for rows A2-A4).
+// Step 1 (cgat_edge_attn_bwd_prep, edge_attn_fwd.cu) leaves per-edge dL/da, dL/dv (E,H,F) and the
+// LeakyReLU sign masks.  Here:
+//
+//  cgat_edge_attn_dgrad   d_hid = dZ W2 (second-layer dgrad) on the tensor cores with HIDDEN UNITS on the
+//      128 TMEM lanes and a tile of 128 edges on the columns, then in the epilogue
+//          d_pre = d_hid * leaky_relu'(pre)         (sign masks: nothing is re-gathered)
+//          G[seg, col] = sum over the segment's edges of d_pre      (thread-sequential, no atomics)
+//      The kernel is run twice: once over edges grouped by DESTINATION (-> dL/dP dst-block) and once over
+//      edges grouped by SOURCE (-> dL/dP src-block and, run-length accumulated, dL/dT per shell rank).
+//      Two passes cost one extra dgrad GEMM but keep every reduction deterministic and conflict-free.
+//
+//  cgat_edge_attn_wgrad   dW2[net,h] = dZ^T hid: the contraction runs over EDGES, so both operands are
+//      staged MN-major (dZ rows as they are, hid rows re-gathered exactly like the forward); split over
+//      (net, head) x edge ranges, partial results summed by the caller.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cgat {
+namespace {
+using namespace tc;
+
+constexpr int kBT = 128;  // edges per tile
+constexpr int kBF = 128;  // channels per head (instantiated for F = 128)
+constexpr int kBProducers = 256;
+constexpr int kBThreads = 128 + kBProducers + 32;
+constexpr int kBStages = 3;
+constexpr int kBStageBytes = 2 * (int)kPackStageBytes;
+constexpr int kBMetaBufs = 4;
+constexpr int kBMetaBytes = kBMetaBufs * 3 * kBT * 4;
+constexpr int kBMaxRanks = 32;
+constexpr int kBRankBytes = kBMaxRanks * 128 * 4;
+constexpr int kBSmemBytes = kBStages * kBStageBytes + kBMetaBytes + kBRankBytes + 256 + 1024;
+
+struct DgradArgs {
+  const float* d_gate;     // (E, H, F) rows in destination-sorted order
+  const float* d_msg;
+  const uint32_t* signs;   // [2][H][kcn][E]
+  const int32_t* segptr;   // (N+1) CSR pointer of THIS edge order
+  const int32_t* seg;      // (E) segment id of each edge of this order
+  const int32_t* row;      // (E) destination-sorted row of each edge of this order, or null (identity)
+  const int32_t* rnk;      // (E) shell rank of each edge of this order (only when d_rank != null)
+  const float* wt_a;       // packed (H*Hd, F): row h*Hd+k, col c = W2A[h*F+c, k]
+  const float* wt_m;
+  float* G;                // (N, ldg); this pass writes columns [col_off, col_off + 2*H*Hd)
+  float* d_rank;           // (grid, n_ranks, 2*H*Hd) partial dL/dT per CTA, or null
+  int64_t ldg;
+  int col_off, n_atoms, n_edges, heads, hd, n_ranks;
+};
+
+__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int64_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+
+__global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stages = smem;
+  int32_t* meta = reinterpret_cast<int32_t*>(smem + kBStages * kBStageBytes);  // [4][seg|row|rank][128]
+  float* rank_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(meta) + kBMetaBytes);  // [n_ranks][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rank_acc) + kBRankBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kBStages;
+  uint64_t* tmem_full = bars + 2 * kBStages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  int32_t* range = reinterpret_cast<int32_t*>(tmem_slot + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = g.heads, hd = g.hd, hhd = H * hd;
+  const int kcn = (hd + 31) / 32;       // sign words per (net, head, edge)
+  const int nhalf = (hd + 127) / 128;   // M tiles of 128 hidden units per head
+  const int n_items = 2 * H * nhalf;
+  constexpr int kcf = kBF / 32;         // K chunks of the dgrad contraction (over channels)
+
+  if (tid == 0) {
+    for (int s = 0; s < kBStages; ++s) {
+      mbar_init(&full[s], kBProducers);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], 128);
+    }
+    mbar_init_fence();
+    const int G_ = gridDim.x;
+    const int64_t t0 = (int64_t)g.n_edges * blockIdx.x / G_, t1 = (int64_t)g.n_edges * (blockIdx.x + 1) / G_;
+    const int a_lo = lower_bound_i32(g.segptr, g.n_atoms + 1, t0);
+    const int a_hi = (blockIdx.x == G_ - 1) ? g.n_atoms : lower_bound_i32(g.segptr, g.n_atoms + 1, t1);
+    range[0] = g.segptr[a_lo];
+    range[1] = g.segptr[a_hi];
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (tid < 128)
+    for (int r = 0; r < kBMaxRanks; ++r) rank_acc[r * 128 + tid] = 0.f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const int e_lo = range[0], e_hi = range[1];
+  const int n_tiles = (e_hi - e_lo + kBT - 1) / kBT;
+
+  if (warp < 4) {
+    // ---------------------------------------------------------------- epilogue
+    const int c = warp * 32 + lane;
+    const uint32_t bitpos = (uint32_t)((lane & 3) * 8 + (lane >> 2));
+    uint32_t icount = 0;
+    for (int item = 0; item < n_items; ++item) {
+      const int net = item / (H * nhalf), h = (item / nhalf) % H, half = item % nhalf;
+      const int kk = half * 128 + c;
+      const bool kvalid = kk < hd;
+      const int col = net * hhd + h * hd + kk;
+      const uint32_t* sg = g.signs + ((int64_t)(net * H + h) * kcn + (half * 4 + warp)) * g.n_edges;
+      float acc = 0.f, racc = 0.f;
+      int cur = -1, currk = -1;
+      for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
+        const int e0 = e_lo + tile * kBT;
+        const int nv = min(kBT, e_hi - e0);
+        const int32_t* mt = meta + (icount & (kBMetaBufs - 1)) * 3 * kBT;
+        const uint32_t b = icount & 1u;
+        mbar_wait(&tmem_full[b], (icount >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + b * 256;
+#pragma unroll 1
+        for (int cc = 0; cc < kBT / 32; ++cc) {
+          // sign words of these 32 edges first: 32 independent loads in flight (the stores to G below would
+          // otherwise serialise them one column at a time)
+          uint32_t wd[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int t = cc * 32 + j;
+            wd[j] = (kvalid && t < nv) ? __ldg(sg + mt[kBT + t]) : 0u;
+          }
+          float v[32], w[32];
+          tmem_ld32(tbase + cc * 32, v);
+          tmem_ld32(tbase + 128 + cc * 32, w);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int t = cc * 32 + j;
+            if (t < nv) {
+              const int sid = mt[t];
+              const float dp = (v[j] + w[j]) * (((wd[j] >> bitpos) & 1u) ? 1.f : 0.01f);
+              if (sid != cur) {
+                if (cur >= 0 && kvalid) g.G[(int64_t)cur * g.ldg + g.col_off + col] = acc;
+                acc = 0.f, cur = sid;
+              }
+              acc += dp;
+              if (g.d_rank) {
+                const int rk = mt[2 * kBT + t];
+                if (rk != currk) {
+                  if (currk >= 0) rank_acc[currk * 128 + c] += racc;
+                  racc = 0.f, currk = rk;
+                }
+                racc += dp;
+              }
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[b]);
+      }
+      if (cur >= 0 && kvalid) g.G[(int64_t)cur * g.ldg + g.col_off + col] = acc;
+      if (g.d_rank) {
+        if (currk >= 0) rank_acc[currk * 128 + c] += racc;
+        float* dst = g.d_rank + (int64_t)blockIdx.x * g.n_ranks * 2 * hhd + col;
+        for (int r = 0; r < g.n_ranks; ++r) {
+          if (kvalid) dst[(int64_t)r * 2 * hhd] = rank_acc[r * 128 + c];
+          rank_acc[r * 128 + c] = 0.f;
+        }
+      }
+    }
+  } else if (warp < 12) {
+    // ---------------------------------------------------------------- producers
+    const int pt = tid - 128;
+    uint32_t cnt = 0, icount = 0;
+    const uint8_t* wt[2] = {reinterpret_cast<const uint8_t*>(g.wt_a), reinterpret_cast<const uint8_t*>(g.wt_m)};
+    const float* dz[2] = {g.d_gate, g.d_msg};
+    for (int item = 0; item < n_items; ++item) {
+      const int net = item / (H * nhalf), h = (item / nhalf) % H, half = item % nhalf;
+      for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
+        const int e0 = e_lo + tile * kBT;
+        const int nv = min(kBT, e_hi - e0);
+        int32_t* mt = meta + (icount & (kBMetaBufs - 1)) * 3 * kBT;
+        if (pt < kBT) {
+          const bool ok = pt < nv;
+          mt[pt] = ok ? g.seg[e0 + pt] : -1;
+          mt[kBT + pt] = ok ? (g.row ? g.row[e0 + pt] : e0 + pt) : 0;
+          mt[2 * kBT + pt] = (ok && g.rnk) ? g.rnk[e0 + pt] : 0;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kBProducers) : "memory");
+        int64_t rowoff[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int r = (pt + kBProducers * j) >> 3;
+          rowoff[j] = (r < nv) ? ((int64_t)mt[kBT + r] * H + h) * kBF : -1;
+        }
+        for (int kc = 0; kc < kcf; ++kc, ++cnt) {
+          const uint32_t s = cnt % kBStages, u = cnt / kBStages;
+          mbar_wait(&empty[s], (u + 1) & 1u);
+          uint8_t* st = stages + s * kBStageBytes;
+          if (pt == 0) {
+            mbar_expect_tx(&full[s], kPackStageBytes);
+            bulk_g2s(st, wt[net] + ((int64_t)(h * nhalf + half) * kcf + kc) * kPackStageBytes, kPackStageBytes, &full[s]);
+          }
+          float4 x[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cch = (pt + kBProducers * j) & 7;
+            x[j] = rowoff[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(dz[net] + rowoff[j] + kc * 32 + cch * 4))
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint8_t* bh = st + kPackStageBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = pt + kBProducers * j;
+            float4 hi, lo;
+            split_tf32(x[j], hi, lo);
+            const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+            *reinterpret_cast<float4*>(bh + off) = hi;
+            *reinterpret_cast<float4*>(bh + kPackImageBytes + off) = lo;
+          }
+          fence_async_smem();
+          mbar_arrive(&full[s]);
+        }
+      }
+    }
+  } else {
+    // ---------------------------------------------------------------- MMA issuer
+    constexpr uint32_t idesc = umma_idesc_tf32(128, kBT);
+    uint32_t cnt = 0, icount = 0;
+    for (int item = 0; item < n_items; ++item) {
+      for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
+        const uint32_t b = icount & 1u;
+        mbar_wait(&tmem_empty[b], ((icount >> 1) + 1) & 1u);
+        tc_fence_after();
+        const uint32_t d = tmem + b * 256, dc = d + 128;
+        for (int kc = 0; kc < kcf; ++kc, ++cnt) {
+          const uint32_t s = cnt % kBStages, u = cnt / kBStages;
+          mbar_wait(&full[s], u & 1u);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(stages + s * kBStageBytes), a_lo = a_hi + kPackImageBytes;
+            const uint32_t b_hi = a_hi + kPackStageBytes, b_lo = b_hi + kPackImageBytes;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t off = ks * 32;
+              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+            }
+            umma_commit(&empty[s]);
+            if (kc == kcf - 1) umma_commit(&tmem_full[b]);
+          }
+          __syncwarp();
+        }
+      }
+    }
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct WgradArgs {
+  const float* P;
+  const float* T;
+  const int32_t* src;
+  const int32_t* dst;
+  const int32_t* rank;
+  const float* d_gate;
+  const float* d_msg;
+  float* out;  // (n_split, 2, H, F, Hd) partial dW2
+  int n_edges, heads, hd, n_split;
+};
+
+constexpr int kWImage = 32 * 128;          // 32 K-rows (edges) x 128 B
+constexpr int kWAPart = 4 * kWImage;       // dZ: 128 channels = 4 images
+constexpr int kWBPart = 8 * kWImage;       // hid: up to 256 hidden units = 8 images
+constexpr int kWStageBytes = 2 * kWAPart + 2 * kWBPart;  // 96 KB
+constexpr int kWStages = 2;
+constexpr int kWSmemBytes = kWStages * kWStageBytes + 2 * 3 * 32 * 4 + 256 + 1024;
+
+__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
+
+__global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArgs g) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* stages = smem;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kWStages * kWStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kWStages;
+  uint64_t* accum = bars + 2 * kWStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  int32_t* meta = reinterpret_cast<int32_t*>(tmem_slot + 2);  // [2 parity][3][32]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int H = g.heads, hd = g.hd, hhd = H * hd;
+  const int item = blockIdx.x / g.n_split, split = blockIdx.x % g.n_split;
+  const int net = item / H, h = item % H;
+  const int e_lo = (int)((int64_t)g.n_edges * split / g.n_split), e_hi = (int)((int64_t)g.n_edges * (split + 1) / g.n_split);
+  const int n_chunks = (e_hi - e_lo + 31) / 32;
+  const int64_t ldp = 4 * (int64_t)hhd, ldt = 2 * (int64_t)hhd;
+
+  if (tid == 0) {
+    for (int s = 0; s < kWStages; ++s) {
+      mbar_init(&full[s], kBProducers);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    mbar_init_fence();
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    // epilogue: one accumulation over the whole edge range, written once
+    const int c = warp * 32 + lane;
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    float* dst = g.out + ((((int64_t)split * 2 + net) * H + h) * kBF + c) * hd;
+#pragma unroll 1
+    for (int cc = 0; cc < 8; ++cc) {
+      float v[32], w[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 256 + cc * 32, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (cc * 32 + j < hd) dst[cc * 32 + j] = n_chunks > 0 ? v[j] + w[j] : 0.f;
+    }
+    tc_fence_before();
+  } else if (warp < 12) {
+    const int pt = tid - 128;
+    const float* dz = net ? g.d_msg : g.d_gate;
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int s = ch % kWStages, u = ch / kWStages;
+      const int e0 = e_lo + ch * 32;
+      const int nv = min(32, e_hi - e0);
+      int32_t* mt = meta + (ch & 1) * 96;
+      if (pt < 32) {
+        const bool ok = pt < nv;
+        mt[pt] = ok ? g.dst[e0 + pt] : -1;
+        mt[32 + pt] = ok ? g.src[e0 + pt] : 0;
+        mt[64 + pt] = ok ? g.rank[e0 + pt] : 0;
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(kBProducers) : "memory");
+      mbar_wait(&empty[s], (u + 1) & 1u);
+      uint8_t* st = stages + s * kWStageBytes;
+      // A operand: dZ rows (32 edges x 128 channels), MN-major images of 32 channels
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = pt + kBProducers * j, r = idx >> 5, q = idx & 31;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < nv) x = __ldg(reinterpret_cast<const float4*>(dz + ((int64_t)(e0 + r) * H + h) * kBF + q * 4));
+        float4 hi, lo;
+        split_tf32(x, hi, lo);
+        const uint32_t off = (q >> 3) * kWImage + mn_sw128_offset(r, q & 7);
+        *reinterpret_cast<float4*>(st + off) = hi;
+        *reinterpret_cast<float4*>(st + kWAPart + off) = lo;
+      }
+      // B operand: hidden activations (32 edges x Hd), re-gathered like the forward
+      uint8_t* bh = st + 2 * kWAPart;
+#pragma unroll 2
+      for (int j = 0; j < 8; ++j) {
+        const int idx = pt + kBProducers * j, r = idx >> 6, q = idx & 63;
+        const int d = mt[r];
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (d >= 0 && q * 4 < hd) {
+          const int col = net * hhd + h * hd + q * 4;
+          const float4 pd = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)d * ldp + col));
+          const float4 ps = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)mt[32 + r] * ldp + 2 * hhd + col));
+          const float4 te = __ldg(reinterpret_cast<const float4*>(g.T + (int64_t)mt[64 + r] * ldt + col));
+          x.x = lrelu(pd.x + ps.x + te.x), x.y = lrelu(pd.y + ps.y + te.y);
+          x.z = lrelu(pd.z + ps.z + te.z), x.w = lrelu(pd.w + ps.w + te.w);
+        }
+        float4 hi, lo;
+        split_tf32(x, hi, lo);
+        const uint32_t off = (q >> 3) * kWImage + mn_sw128_offset(r, q & 7);
+        *reinterpret_cast<float4*>(bh + off) = hi;
+        *reinterpret_cast<float4*>(bh + kWBPart + off) = lo;
+      }
+      fence_async_smem();
+      mbar_arrive(&full[s]);
+    }
+  } else {
+    const uint32_t idesc = umma_idesc_tf32(128, 256, 1, 1);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int s = ch % kWStages, u = ch / kWStages;
+      mbar_wait(&full[s], u & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(stages + s * kWStageBytes), a_lo = a_hi + kWAPart;
+        const uint32_t b_hi = a_hi + 2 * kWAPart, b_lo = b_hi + kWBPart;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint32_t o = ks * 1024;
+          umma_tf32(tmem + 256, umma_desc_mn_sw128(a_lo + o, kWImage), umma_desc_mn_sw128(b_hi + o, kWImage), idesc,
+                    (ch | ks) != 0);
+          umma_tf32(tmem + 256, umma_desc_mn_sw128(a_hi + o, kWImage), umma_desc_mn_sw128(b_lo + o, kWImage), idesc, 1);
+          umma_tf32(tmem, umma_desc_mn_sw128(a_hi + o, kWImage), umma_desc_mn_sw128(b_hi + o, kWImage), idesc,
+                    (ch | ks) != 0);
+        }
+        umma_commit(&empty[s]);
+        if (ch == n_chunks - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+    if (n_chunks == 0 && lane == 0) mbar_arrive(accum);
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+}  // namespace cgat
+
+using namespace cgat;
+
+extern "C" int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges) {
+  const int64_t tiles = ceil_div(n_edges, kBT);
+  return (int32_t)(tiles < kNumSMs ? (tiles > 0 ? tiles : 1) : kNumSMs);
+}
+
+// One pass of the dgrad + segment reduction.  `segptr/seg/row/rnk` describe the edge order of this pass
+// (grouped by destination or by source).  Writes G[:, col_off : col_off + 2*H*Hd]; rows of atoms without
+// edges in this order are left untouched (zero them beforehand).  d_rank (optional):
+// (cgat_edge_attn_dgrad_grid(E), n_ranks, 2*H*Hd) per-CTA partial sums per shell rank.
+extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t* signs,
+                                    const int32_t* segptr, const int32_t* seg, const int32_t* row, const int32_t* rnk,
+                                    const float* wt_a_packed, const float* wt_m_packed, float* G, int64_t ldg,
+                                    int32_t col_off, float* d_rank, int32_t n_ranks, int64_t n_atoms, int64_t n_edges,
+                                    int32_t heads, int32_t f, int32_t hd, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (f != kBF) return fail(-2, "cgat_edge_attn_dgrad: only F = 128 is instantiated");
+  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 127))
+    return fail(-2, "cgat_edge_attn_dgrad: heads must be in [1,8] and the hidden width a multiple of 128");
+  if (d_rank && (n_ranks < 1 || n_ranks > kBMaxRanks)) return fail(-2, "cgat_edge_attn_dgrad: n_ranks must be <= 32");
+  if (n_atoms <= 0 || n_edges <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    configured = true;
+  }
+  DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, ldg,
+              col_off, (int)n_atoms, (int)n_edges, heads, hd, n_ranks};
+  edge_dgrad_kernel<<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
+  return check_launch("edge_dgrad_kernel");
+}
+
+extern "C" int32_t cgat_edge_attn_wgrad_splits(int32_t heads) {
+  int s = kNumSMs / (2 * heads);
+  return s < 1 ? 1 : s;
+}
+
+// out: (cgat_edge_attn_wgrad_splits(H), 2, H, F, Hd) partial dL/dW2 (gate net, message net); sum over dim 0.
+extern "C" int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
+                                    const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
+                                    int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (f != kBF) return fail(-2, "cgat_edge_attn_wgrad: only F = 128 is instantiated");
+  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 15) || hd > 256)
+    return fail(-2, "cgat_edge_attn_wgrad: hidden width must be a multiple of 16, at most 256");
+  if (n_edges <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(edge_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes));
+    configured = true;
+  }
+  const int n_split = cgat_edge_attn_wgrad_splits(heads);
+  WgradArgs a{P, T, src, dst, rank, d_gate, d_msg, out, (int)n_edges, heads, hd, n_split};
+  edge_wgrad_kernel<<<2 * heads * n_split, kBThreads, kWSmemBytes, stream>>>(a);
+  return check_launch("edge_wgrad_kernel");
+}

@@ -52,9 +52,13 @@ struct EdgeArgs {
   const float* w2m;
   const float* b2a;     // (H*F)
   const float* b2m;
-  float* out;           // (N, H, F)
-  float* smax;          // (N, H, F) or null
+  float* out;           // (N, H, F)   forward: written; backward-prep: read
+  float* smax;          // (N, H, F)   forward: written if non-null; backward-prep: read
   float* sden;
+  const float* g_out;   // backward-prep: dL/d out (N, H, F)
+  float* d_gate;        // backward-prep: dL/d a_t,h (E, H, F), destination-sorted edge order
+  float* d_msg;         // backward-prep: dL/d v_t,h (E, H, F)
+  uint32_t* signs;      // backward-prep: [2][H][kcn][E] LeakyReLU side of the 32 hidden units of a chunk
   int n_atoms, n_edges, heads, hd;
   float eps;
 };
@@ -74,7 +78,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
 
-__global__ void __launch_bounds__(kEThreads, 1) edge_attn_fwd_kernel(const EdgeArgs g) {
+// kMode 0: forward (segmented online softmax, writes out / max / den)
+// kMode 1: backward-prep: recompute a, v and emit  d_msg = alpha * g,  d_gate = alpha * (v - out) * g  per edge
+//          (alpha from the saved per-segment max / den) plus the sign masks of the hidden pre-activations.
+template <int kMode>
+__global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
@@ -119,7 +127,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_fwd_kernel(const EdgeA
   const int n_tiles = (e_hi - e_lo + kET - 1) / kET;
 
   if (warp < 4) {
-    // ---------------------------------------------------------------- epilogue: segmented softmax
+    // ---------------------------------------------------------------- epilogue
     const int c = warp * 32 + lane;  // channel = TMEM lane
     uint32_t hcount = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
@@ -130,11 +138,10 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_fwd_kernel(const EdgeA
       for (int h = 0; h < H; ++h, ++hcount) {
         const uint32_t hb = hcount & 1u;
         float* cs = carry + (h * 4) * kEF;
-        float m, den, acc;
-        int d;
-        if (tile == 0) {
-          m = -INFINITY, den = 0.f, acc = 0.f, d = -1;
-        } else {
+        float m = -INFINITY, den = 0.f, acc = 0.f;  // kMode 1 reuses them as (seg max, 1/(den+eps), out) of the open segment
+        float gg = 0.f;
+        int d = -1;
+        if (kMode == 0 && tile > 0) {
           m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = __float_as_int(cs[3 * kEF + c]);
         }
         const float ba = __ldg(g.b2a + h * kEF + c), bm = __ldg(g.b2m + h * kEF + c);
@@ -152,33 +159,50 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_fwd_kernel(const EdgeA
             const int t = cc * 32 + j;
             if (t < nv) {
               const int dc = mdst[t];
-              if (dc != d) {
-                if (d >= 0) {
-                  const int64_t o = ((int64_t)d * H + h) * kEF + c;
-                  g.out[o] = acc / (den + g.eps);
-                  if (g.smax) g.smax[o] = m, g.sden[o] = den;
-                }
-                m = -INFINITY, den = 0.f, acc = 0.f, d = dc;
-              }
               const float a = av[j] + ba, v = vv[j] + bm;
-              const float mn = fmaxf(m, a);
-              const float r = expf(m - mn), p = expf(a - mn);
-              den = den * r + p;
-              acc = acc * r + p * v;
-              m = mn;
+              if (kMode == 0) {
+                if (dc != d) {
+                  if (d >= 0) {
+                    const int64_t o = ((int64_t)d * H + h) * kEF + c;
+                    g.out[o] = acc / (den + g.eps);
+                    if (g.smax) g.smax[o] = m, g.sden[o] = den;
+                  }
+                  m = -INFINITY, den = 0.f, acc = 0.f, d = dc;
+                }
+                const float mn = fmaxf(m, a);
+                const float r = expf(m - mn), p = expf(a - mn);
+                den = den * r + p;
+                acc = acc * r + p * v;
+                m = mn;
+              } else {
+                if (dc != d) {
+                  const int64_t o = ((int64_t)dc * H + h) * kEF + c;
+                  m = __ldg(g.smax + o);
+                  den = 1.f / (__ldg(g.sden + o) + g.eps);
+                  acc = __ldg(g.out + o);
+                  gg = __ldg(g.g_out + o);
+                  d = dc;
+                }
+                const float alpha = expf(a - m) * den;
+                const int64_t o = ((int64_t)(e0 + t) * H + h) * kEF + c;
+                g.d_msg[o] = alpha * gg;
+                g.d_gate[o] = alpha * (v - acc) * gg;
+              }
             }
           }
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[hb]);
-        if (last_tile) {
-          if (d >= 0) {
-            const int64_t o = ((int64_t)d * H + h) * kEF + c;
-            g.out[o] = acc / (den + g.eps);
-            if (g.smax) g.smax[o] = m, g.sden[o] = den;
+        if (kMode == 0) {
+          if (last_tile) {
+            if (d >= 0) {
+              const int64_t o = ((int64_t)d * H + h) * kEF + c;
+              g.out[o] = acc / (den + g.eps);
+              if (g.smax) g.smax[o] = m, g.sden[o] = den;
+            }
+          } else {
+            cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc, cs[3 * kEF + c] = __int_as_float(d);
           }
-        } else {
-          cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc, cs[3 * kEF + c] = __int_as_float(d);
         }
       }
     }
@@ -235,10 +259,23 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_fwd_kernel(const EdgeA
             for (int j = 0; j < 4; ++j) {
               const int idx = pt + kEProducers * j;
               float4 x;
-              x.x = lrelu(pd[j].x + ps[j].x + te[j].x);
-              x.y = lrelu(pd[j].y + ps[j].y + te[j].y);
-              x.z = lrelu(pd[j].z + ps[j].z + te[j].z);
-              x.w = lrelu(pd[j].w + ps[j].w + te[j].w);
+              x.x = pd[j].x + ps[j].x + te[j].x;
+              x.y = pd[j].y + ps[j].y + te[j].y;
+              x.z = pd[j].z + ps[j].z + te[j].z;
+              x.w = pd[j].w + ps[j].w + te[j].w;
+              if (kMode == 1) {
+                // which side of the LeakyReLU each hidden pre-activation is on: byte j' = component j' of the
+                // float4, bit c = 16-byte chunk c of the 128-byte row  ->  hidden unit c*4 + j' of this K chunk
+                const uint32_t b0 = __ballot_sync(0xffffffffu, x.x > 0.f), b1 = __ballot_sync(0xffffffffu, x.y > 0.f);
+                const uint32_t b2 = __ballot_sync(0xffffffffu, x.z > 0.f), b3 = __ballot_sync(0xffffffffu, x.w > 0.f);
+                const int sh = lane & 24;  // the 8 lanes that share an edge row
+                const uint32_t word = ((b0 >> sh) & 0xFFu) | (((b1 >> sh) & 0xFFu) << 8) | (((b2 >> sh) & 0xFFu) << 16) |
+                                      (((b3 >> sh) & 0xFFu) << 24);
+                const int r = idx >> 3;
+                if ((lane & 7) == 0 && r < nv)
+                  g.signs[((int64_t)(net * H + h) * kcn + kc) * g.n_edges + e0 + r] = word;
+              }
+              x.x = lrelu(x.x), x.y = lrelu(x.y), x.z = lrelu(x.z), x.w = lrelu(x.w);
               float4 hi, lo;
               split_tf32(x, hi, lo);
               const uint32_t off = sw128_offset(idx >> 3, idx & 7);
@@ -297,16 +334,36 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_fwd_kernel(const EdgeA
 
 using namespace cgat;
 
+namespace {
+int check_edge_args(int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd) {
+  if (f != kEF) return fail(-2, "cgat_edge_attn_*: only F = 128 (vector attention) is instantiated");
+  if (heads < 1 || heads > kEMaxHeads) return fail(-2, "cgat_edge_attn_*: heads must be in [1,8]");
+  if (hd <= 0 || (hd & 3)) return fail(-2, "cgat_edge_attn_*: hidden width must be a multiple of 4");
+  if (n_atoms >= (1ll << 31) - 1 || n_edges >= (1ll << 31) - 129) return fail(-2, "cgat_edge_attn_*: size overflow");
+  return 0;
+}
+
+template <int kMode>
+int launch_edge(const EdgeArgs& a, cudaStream_t stream) {
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(edge_attn_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kESmemBytes));
+    configured = true;
+  }
+  const int64_t tiles = ceil_div(a.n_edges, kET);
+  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
+  edge_attn_kernel<kMode><<<grid, kEThreads, kESmemBytes, stream>>>(a);
+  return check_launch(kMode == 0 ? "edge_attn_fwd_kernel" : "edge_attn_bwd_prep_kernel");
+}
+}  // namespace
+
 extern "C" int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
                                   const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                                   const float* w2m_packed, const float* b2a, const float* b2m, float* out,
                                   float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
                                   int32_t f, int32_t hd, float eps, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (f != kEF) return fail(-2, "cgat_edge_attn_fwd: only F = 128 (vector attention) is instantiated");
-  if (heads < 1 || heads > kEMaxHeads) return fail(-2, "cgat_edge_attn_fwd: heads must be in [1,8]");
-  if (hd <= 0 || (hd & 3)) return fail(-2, "cgat_edge_attn_fwd: hidden width must be a multiple of 4");
-  if (n_atoms >= (1ll << 31) - 1 || n_edges >= (1ll << 31) - 129) return fail(-2, "cgat_edge_attn_fwd: size overflow");
+  if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
   if (n_atoms <= 0) return 0;
   const size_t out_bytes = sizeof(float) * (size_t)n_atoms * heads * f;
   CGAT_CUDA(cudaMemsetAsync(out, 0, out_bytes, stream));  // atoms without in-edges aggregate to 0
@@ -315,15 +372,25 @@ extern "C" int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t*
     CGAT_CUDA(cudaMemsetAsync(seg_den, 0, out_bytes, stream));
   }
   if (n_edges <= 0) return 0;
-  static bool configured = false;
-  if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(edge_attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kESmemBytes));
-    configured = true;
-  }
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
+             nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
+  return launch_edge<0>(a, stream);
+}
+
+// Backward, step 1: per-edge gradients of the second-layer outputs.  Recomputes a_t,h / v_t,h exactly like
+// the forward and writes d_gate, d_msg (E, H, F) in destination-sorted edge order plus the LeakyReLU sign
+// masks signs[2][H][ceil(hd/32)][E] that the dgrad kernel needs (32 hidden units per word).
+extern "C" int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                                       const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                                       const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
+                                       const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
+                                       float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                       int32_t f, int32_t hd, float eps, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
+  if (n_atoms <= 0 || n_edges <= 0) return 0;
+  EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
+             const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs,
              (int)n_atoms, (int)n_edges, heads, hd, eps};
-  const int64_t tiles = ceil_div(n_edges, kET);
-  const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  edge_attn_fwd_kernel<<<grid, kEThreads, kESmemBytes, stream>>>(a);
-  return check_launch("edge_attn_fwd_kernel");
+  return launch_edge<1>(a, stream);
 }

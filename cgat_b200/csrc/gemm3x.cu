@@ -179,6 +179,124 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// C[M,N] = sum_k A[k,m] * B[k,n]  (A: [K x M], B: [K x N], both row-major): the weight-gradient shape
+// dW = dY^T X, where the contraction runs over the ROWS of both operands.  Both operands are staged
+// MN-major (no transposes anywhere): a K-chunk of 32 rows becomes four 32-column images per operand.
+// One 128 x 128 tile per CTA; split-K over blockIdx.z writes partial tiles that the caller sums.
+constexpr int kTnImage = 32 * 128;  // 32 K-rows x 128 B
+
+__device__ __forceinline__ void stage_chunk_mn(const float* __restrict__ src, int64_t ld, int col0, int n_cols,
+                                               int k0, int k_end, uint8_t* hi, uint8_t* lo, int tid) {
+  float4 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = tid + kWorkers * j, r = idx >> 5, q = idx & 31;
+    const int gk = k0 + r, gc = col0 + q * 4;
+    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gk < k_end && gc < n_cols) v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)gk * ld + gc));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int idx = tid + kWorkers * j, r = idx >> 5, q = idx & 31;
+    const uint32_t off = (q >> 3) * kTnImage + mn_sw128_offset(r, q & 7);
+    float4 h, l;
+    split_tf32(v[j], h, l);
+    *reinterpret_cast<float4*>(hi + off) = h;
+    *reinterpret_cast<float4*>(lo + off) = l;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm3x_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
+                 float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int N, int K, int k_per_split) {
+  constexpr int kStages = 3, kOp = 4 * kTnImage;  // 16 KB per operand part
+  constexpr int kStageBytes = 4 * kOp;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* accum = bars + 2 * kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const int nk = (k_end - k_begin + kKC - 1) / kKC;
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full[s], kWorkers);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum, 1);
+    mbar_init_fence();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (warp < 4) {
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % kStages, u = kc / kStages;
+      mbar_wait(&empty[s], (u + 1) & 1);
+      uint8_t* st = smem + s * kStageBytes;
+      stage_chunk_mn(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + kOp, tid);
+      stage_chunk_mn(B, ldb, n0, N, k_begin + kc * kKC, k_end, st + 2 * kOp, st + 3 * kOp, tid);
+      fence_async_smem();
+      mbar_arrive(&full[s]);
+    }
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    const int m = m0 + warp * 32 + lane;
+    float* cbase = C + (int64_t)blockIdx.z * split_stride;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[32], w[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 128 + cc * 32, w);
+      tmem_ld_wait();
+      if (m < M) {
+        float* crow = cbase + (int64_t)m * ldc + n0 + cc * 32;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + cc * 32 + j < N) crow[j] = nk > 0 ? v[j] + w[j] : 0.f;
+      }
+    }
+    tc_fence_before();
+  } else {
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 128, 1, 1);
+    for (int kc = 0; kc < nk; ++kc) {
+      const int s = kc % kStages, u = kc / kStages;
+      mbar_wait(&full[s], u & 1);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + kOp;
+        const uint32_t b_hi = a_hi + 2 * kOp, b_lo = a_hi + 3 * kOp;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {  // one MMA consumes 8 K-rows = two 512-byte atoms of every image
+          const uint32_t o = ks * 1024;
+          umma_tf32(tmem + 128, umma_desc_mn_sw128(a_lo + o, kTnImage), umma_desc_mn_sw128(b_hi + o, kTnImage), idesc,
+                    (kc | ks) != 0);
+          umma_tf32(tmem + 128, umma_desc_mn_sw128(a_hi + o, kTnImage), umma_desc_mn_sw128(b_lo + o, kTnImage), idesc, 1);
+          umma_tf32(tmem, umma_desc_mn_sw128(a_hi + o, kTnImage), umma_desc_mn_sw128(b_hi + o, kTnImage), idesc,
+                    (kc | ks) != 0);
+        }
+        umma_commit(&empty[s]);
+        if (kc == nk - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+    if (nk == 0 && lane == 0) mbar_arrive(accum);
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 256);
+  }
+}
+
 template <int BN>
 int launch_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
                 int M, int N, int K, int act, cudaStream_t stream) {
@@ -208,4 +326,28 @@ extern "C" int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64
   if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return fail(-2, "cgat_gemm3x_nt: size overflow");
   if (N <= 64) return launch_gemm<64>(A, lda, B, ldb, bias, C, ldc, (int)M, (int)N, (int)K, act, stream);
   return launch_gemm<128>(A, lda, B, ldb, bias, C, ldc, (int)M, (int)N, (int)K, act, stream);
+}
+
+// C[split][M,N] = sum over this split's rows k of A[k,m] * B[k,n].  n_split partial results, `split_stride`
+// floats apart (the caller sums them: keeps the K/8-step accumulation short and fills the SMs).
+extern "C" int cgat_gemm3x_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                              int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M <= 0 || N <= 0 || n_split <= 0) return 0;
+  if ((M & 3) || (N & 3) || (lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15))
+    return fail(-2, "cgat_gemm3x_tn: M, N, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return fail(-2, "cgat_gemm3x_tn: size overflow");
+  constexpr int kSmem = 3 * 4 * 4 * kTnImage + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
+    configured = true;
+  }
+  int k_per_split = (int)ceil_div(ceil_div(K, n_split), kKC) * kKC;
+  if (k_per_split == 0) k_per_split = kKC;
+  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, 128), (unsigned)n_split);
+  gemm3x_tn_kernel<<<grid, kThreads, kSmem, stream>>>(A, lda, B, ldb, C, ldc, split_stride, (int)M, (int)N, (int)K,
+                                                      k_per_split);
+  return check_launch("gemm3x_tn_kernel");
 }

@@ -37,7 +37,12 @@ struct HyperCfg {
   static constexpr int kTmemCols = 4 * F;
 };
 
-template <int F>
+// kMode 0 (forward):   y_out[n,o] = sum_j D_o[n,j] * y_in[n,j] + e_term[n,o]
+// kMode 1 (backward):  partial[chunk][n,j] = sum_{o in chunk} y_in[n,o] * D_o[n,j]      (y_in carries dL/dy_out)
+//   with D_o[n,j] = sum_m z[n,m] Wblk_o[j,m].  Backward uses it twice: (z, W blocks) -> dL/dy_in and
+//   (y, transposed W blocks) -> dL/dz, i.e. both activation gradients of the hyper-linear layer without ever
+//   forming the (N, F*F) predicted-weight tensor or its gradient.
+template <int F, int kMode>
 __global__ void __launch_bounds__(HyperCfg<F>::kThreads, 1)
 hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
                         const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
@@ -87,31 +92,40 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
       const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
       const int n = tile * 128 + warp * 32 + lane;
       const bool valid = n < n_atoms;
-      float y[F];
+      float y[F];  // kMode 0: this atom's y_in row; kMode 1: the running partial sums over o
 #pragma unroll
       for (int j = 0; j < F / 4; ++j) {
-        float4 t = valid ? __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F) + j)
-                         : make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F) + j);
         y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
       }
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
         const int o = chunk * oc + oi;
         const uint32_t b = ocount & 1u;
+        const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
         mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
         tc_fence_after();
         float acc = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < F / 32; ++cc) {
-          float v[32], w[32];
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + cc * 32, v);
-          tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + F + cc * 32, w);
+        for (int cc = 0; cc < F / 16; ++cc) {
+          float v[16], w[16];
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + cc * 16, v);
+          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + F + cc * 16, w);
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) acc = fmaf(v[j] + w[j], y[cc * 32 + j], acc);
+          for (int j = 0; j < 16; ++j) {
+            if (kMode == 0) acc = fmaf(v[j] + w[j], y[cc * 16 + j], acc);
+            else y[cc * 16 + j] = fmaf(v[j] + w[j], sc, y[cc * 16 + j]);
+          }
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[b]);
-        if (valid) y_out[(int64_t)n * F + o] = acc + __ldg(e_term + (int64_t)n * F + o);
+        if (kMode == 0 && valid) y_out[(int64_t)n * F + o] = acc + __ldg(e_term + (int64_t)n * F + o);
+      }
+      if (kMode == 1 && valid) {
+        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F);
+#pragma unroll
+        for (int j = 0; j < F / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
       }
     }
   } else if (warp < 8) {
@@ -207,28 +221,52 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
 
 using namespace cgat;
 
-// y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) y_in[n,i] + e_term[n,o]
-//   z, y_in, e_term, y_out: (n_atoms, F) fp32 contiguous; w_packed: cgat_pack_kmajor of W[:F*F, :F]
-extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
-                                     float* y_out, int64_t n_atoms, int32_t f, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
+namespace {
+// output channels per work item: smaller chunks when there are few atom tiles, so that all SMs get work
+int hyper_chunk(int64_t n_atoms, int f) {
+  const int n_tiles = (int)((n_atoms + 127) / 128);
+  int oc = 16;
+  while (oc > 4 && (int64_t)n_tiles * (f / oc) < 3 * kNumSMs) oc >>= 1;
+  return oc;
+}
+
+template <int kMode>
+int launch_hyper(const float* z, const float* y_in, const float* e_term, const float* w_packed, float* y_out,
+                 int64_t n_atoms, int32_t f, cudaStream_t stream) {
   if (n_atoms <= 0) return 0;
-  if (f != 128) return fail(-2, "cgat_hyper_rowdot_fwd: only F = 128 is instantiated");
-  if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_rowdot_fwd: too many atoms");
+  if (f != 128) return fail(-2, "cgat_hyper_*: only F = 128 is instantiated");
+  if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_*: too many atoms");
   using Cfg = HyperCfg<128>;
   static bool configured = false;
   if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_fwd_kernel<128, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
   const int n_tiles = (int)((n_atoms + 127) / 128);
-  // output channels per work item: smaller chunks when there are few atom tiles, so that all SMs get work
-  int oc = 16;
-  while (oc > 4 && (int64_t)n_tiles * (f / oc) < 3 * kNumSMs) oc >>= 1;
+  const int oc = hyper_chunk(n_atoms, f);
   const int n_items = n_tiles * (f / oc);
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  hyper_rowdot_fwd_kernel<128><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(z, y_in, e_term, w_packed, y_out,
-                                                                                  (int)n_atoms, oc);
-  return check_launch("hyper_rowdot_fwd_kernel");
+  hyper_rowdot_fwd_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(z, y_in, e_term, w_packed, y_out,
+                                                                                         (int)n_atoms, oc);
+  return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");
+}
+}  // namespace
+
+// y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) y_in[n,i] + e_term[n,o]
+//   z, y_in, e_term, y_out: (n_atoms, F) fp32 contiguous; w_packed: cgat_pack_kmajor of W[:F*F, :F]
+extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
+                                     float* y_out, int64_t n_atoms, int32_t f, void* stream_) {
+  return launch_hyper<0>(z, y_in, e_term, w_packed, y_out, n_atoms, f, (cudaStream_t)stream_);
+}
+
+// number of partial results cgat_hyper_rowscale writes for this problem size
+extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { return f / hyper_chunk(n_atoms, f); }
+
+// partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m]);  sum over c = the result.
+//   a, scale: (n_atoms, F); w_packed: cgat_pack_kmajor of the F blocks Wblk_o (F x F each, stacked);
+//   partial: (cgat_hyper_rowscale_parts, n_atoms, F)
+extern "C" int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_packed, float* partial,
+                                   int64_t n_atoms, int32_t f, void* stream_) {
+  return launch_hyper<1>(a, scale, nullptr, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
 }

@@ -21,7 +21,11 @@ __global__ void pack_kmajor_kernel(const float* __restrict__ w, int64_t ld, int 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       float x = 0.f;
-      if (gr < rows && gk + j < k) x = transpose ? w[(int64_t)(gk + j) * ld + gr] : w[(int64_t)gr * ld + gk + j];
+      if (gr < rows && gk + j < k) {
+        if (transpose == 0) x = w[(int64_t)gr * ld + gk + j];
+        else if (transpose == 1) x = w[(int64_t)(gk + j) * ld + gr];
+        else x = w[((int64_t)rt * kPackRows + gk + j) * ld + r];  // 2: transpose inside each 128 x 128 block
+      }
       v[j] = x;
     }
     float4 hi, lo;
@@ -39,11 +43,13 @@ using namespace cgat;
 
 extern "C" int64_t cgat_packed_floats(int64_t rows, int64_t k) { return tc::packed_floats(rows, k); }
 
-// w: [rows x k] (transpose=0, leading dimension ld) or its transpose stored as [k x rows] (transpose=1).
+// w: [rows x k] (transpose=0, leading dimension ld), its transpose stored as [k x rows] (transpose=1), or
+// a stack of 128 x 128 blocks each of which is transposed (transpose=2; needs k == 128, rows % 128 == 0).
 extern "C" int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
                                 void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows <= 0 || k <= 0) return 0;
+  if (transpose == 2 && (k != tc::kPackRows || rows % tc::kPackRows)) return fail(-2, "cgat_pack_kmajor: block transpose needs 128 x 128 blocks");
   dim3 grid((unsigned)ceil_div(k, tc::kPackChunk), (unsigned)ceil_div(rows, tc::kPackRows));
   pack_kmajor_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, out);
   return check_launch("pack_kmajor_kernel");

@@ -76,6 +76,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- UMMA descriptors -------------------------------------------------------------------------
@@ -95,18 +106,44 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the contiguous dimension of the source is M or N, the contraction runs over rows).
+// For 32-bit (tf32) elements the only swizzled MN-major layout is SWIZZLE_128B_BASE32B
+// (cutlass/gemm/collective/builders/sm100_common.inl:92; cute Layout_MN_SW128_32B_Atom =
+// Swizzle<2,5,2> o (1024 bits x 4)): a stage is a stack of images, one per block of 32 consecutive
+// M/N elements; an image holds the K rows of that block, 128 bytes each; atoms are 4 rows (512 B) and
+// inside an atom the 32-byte unit u of row r sits at unit (u ^ (r & 3)).
+// LBO = byte distance between images (next 32 M/N elements), SBO = byte distance between 4-row K groups.
+constexpr uint32_t kMnAtomBytes = 512;
+
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(kMnAtomBytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;  // layout type SWIZZLE_128B_BASE32B
+  return d;
+}
+// byte offset, inside an image, of the 16-byte chunk `chunk16` (0..7) of K row r
+__device__ __forceinline__ uint32_t mn_sw128_offset(uint32_t r, uint32_t chunk16) {
+  return r * kSwizzleRowBytes + ((((chunk16 >> 1) ^ (r & 3u)) << 5) | ((chunk16 & 1u) << 4));
+}
+
 // byte offset of fp32 element (row r, k) of a K-major SW128 tile whose K extent is 32 floats
 __device__ __forceinline__ uint32_t sw128_offset(uint32_t r, uint32_t chunk16) {
   return r * kSwizzleRowBytes + ((chunk16 ^ (r & 7u)) << 4);
 }
 
 // kind::tf32, fp32 accumulate, both operands K-major (cute/arch/mma_sm100_desc.hpp: InstrDescriptor)
-__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t m, uint32_t n) {
-  return (1u << 4)            // c_format  = F32
-         | (2u << 7)          // a_format  = TF32
-         | (2u << 10)         // b_format  = TF32
-         | ((n >> 3) << 17)   // N / 8
-         | ((m >> 4) << 24);  // M / 16
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(uint32_t m, uint32_t n, uint32_t a_mn_major = 0,
+                                                       uint32_t b_mn_major = 0) {
+  return (1u << 4)               // c_format  = F32
+         | (2u << 7)             // a_format  = TF32
+         | (2u << 10)            // b_format  = TF32
+         | (a_mn_major << 15)    // A: 0 = K-major, 1 = MN-major
+         | (b_mn_major << 16)    // B: 0 = K-major, 1 = MN-major
+         | ((n >> 3) << 17)      // N / 8
+         | ((m >> 4) << 24);     // M / 16
 }
 
 // D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread for the whole CTA

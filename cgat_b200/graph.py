@@ -15,6 +15,16 @@ from . import _lib
 
 
 @dataclass
+class SourceOrder:
+    """The same edges grouped by SOURCE atom (backward only: dL/dP src-block and dL/dT are sums over the
+    out-edges of an atom / the edges of a rank)."""
+    rowptr: torch.Tensor    # (N+1,) int32
+    seg: torch.Tensor       # (E,) int32  source atom of each src-sorted edge
+    row: torch.Tensor       # (E,) int32  position of that edge in the destination-sorted order
+    rank: torch.Tensor      # (E,) int32
+
+
+@dataclass
 class EdgePlan:
     n_nodes: int
     n_edges: int
@@ -23,6 +33,18 @@ class EdgePlan:
     src: torch.Tensor       # (E,) int32  source atom of each dst-sorted edge
     dst: torch.Tensor       # (E,) int32  destination atom (= segment id)
     rank: torch.Tensor      # (E,) int32  shell rank of each dst-sorted edge
+    edge_index: torch.Tensor = None
+    edge_attr: torch.Tensor = None
+    _by_source: SourceOrder = None
+
+    def by_source(self) -> SourceOrder:
+        if self._by_source is None:
+            flipped = _csr(self.edge_index.flip(0).contiguous(), self.edge_attr, self.n_nodes)
+            perm_s, rowptr_s, _, seg_s, rank_s = flipped
+            inv = torch.empty_like(self.perm)
+            inv[self.perm.long()] = torch.arange(self.n_edges, dtype=torch.int32, device=self.perm.device)
+            self._by_source = SourceOrder(rowptr_s, seg_s, inv[perm_s.long()].contiguous(), rank_s)
+        return self._by_source
 
 
 @dataclass
@@ -33,12 +55,7 @@ class SegmentPlan:
     index: torch.Tensor     # (n_rows,) int32
 
 
-def build_edge_plan(edge_index: torch.Tensor, edge_attr: torch.Tensor, n_nodes: int) -> EdgePlan:
-    """edge_index (2,E) int64 [source; destination] (reference CGAT/data.py:140), edge_attr (E,) int64."""
-    if edge_index.dtype != torch.int64 or edge_attr.dtype != torch.int64:
-        raise TypeError("edge_index / edge_attr must be int64 (the reference's layout)")
-    edge_index = edge_index.contiguous()
-    edge_attr = edge_attr.contiguous()
+def _csr(edge_index, edge_attr, n_nodes):
     dev = edge_index.device
     E = edge_index.shape[1]
     lib = _lib.load()
@@ -50,7 +67,17 @@ def build_edge_plan(edge_index: torch.Tensor, edge_attr: torch.Tensor, n_nodes: 
     _lib.call("cgat_csr_build", _lib.ptr(edge_index), _lib.ptr(edge_attr), E, n_nodes, _lib.ptr(perm),
               _lib.ptr(rowptr), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(rank), _lib.ptr(ws), ws_bytes,
               _lib.stream())
-    return EdgePlan(n_nodes, E, perm, rowptr, src, dst, rank)
+    return perm, rowptr, src, dst, rank
+
+
+def build_edge_plan(edge_index: torch.Tensor, edge_attr: torch.Tensor, n_nodes: int) -> EdgePlan:
+    """edge_index (2,E) int64 [source; destination] (reference CGAT/data.py:140), edge_attr (E,) int64."""
+    if edge_index.dtype != torch.int64 or edge_attr.dtype != torch.int64:
+        raise TypeError("edge_index / edge_attr must be int64 (the reference's layout)")
+    edge_index = edge_index.contiguous()
+    edge_attr = edge_attr.contiguous()
+    perm, rowptr, src, dst, rank = _csr(edge_index, edge_attr, n_nodes)
+    return EdgePlan(n_nodes, edge_index.shape[1], perm, rowptr, src, dst, rank, edge_index, edge_attr)
 
 
 def build_segment_plan(index: torch.Tensor, n_seg: int) -> SegmentPlan:

@@ -78,6 +78,7 @@ def seg_softmax(gate, value, plan: SegmentPlan | None = None, *, ptr=None, seg_o
 LEAKY_SLOPE = 0.01
 # numerics A/B switch for development (1 = fused tensor-core kernels; 0 = library GEMMs + segment kernels)
 _FUSED = os.environ.get("CGAT_B200_FUSED", "1") != "0"
+_TN_WGRAD = os.environ.get("CGAT_B200_TN", "1") != "0"   # weight gradients on cgat_gemm3x_tn vs library mm
 
 
 def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
@@ -137,6 +138,22 @@ def gemm3x(a, w, bias=None, act=0, out=None):
     return out
 
 
+def gemm3x_tn(a, b, n_split=None):
+    """a.T @ b on the tensor cores (cgat_gemm3x_tn): a (K,M), b (K,N) row-contiguous -> (M,N).  The
+    weight-gradient shape: contraction over the rows (atoms / edges) of both operands."""
+    K, M = a.shape
+    N = b.shape[1]
+    if a.stride(1) != 1 or b.stride(1) != 1 or not a.is_cuda:
+        raise ValueError("gemm3x_tn needs row-contiguous CUDA operands")
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if n_split is None:
+        n_split = max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+    part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
+    _lib.call("cgat_gemm3x_tn", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), part.data_ptr(), N, M * N,
+              M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_tn", bound="tensor", flops=2.0 * M * N * K))
+    return part[0] if n_split == 1 else part.sum(dim=0)
+
+
 def packed_kmajor(w, rows=None, transpose=False):
     """Pre-split / pre-swizzled copy of w[:rows] (2-D view of a contiguous weight) for the fused
     kernels.  Cached ON the tensor object and keyed by its autograd version counter, so an in-place
@@ -145,12 +162,12 @@ def packed_kmajor(w, rows=None, transpose=False):
     w2 = w.detach().view(w.shape[0], -1)
     rows = w2.shape[0] if rows is None else rows
     cache = w.__dict__.setdefault("_cgat_packed", {})
-    key = (rows, transpose)
+    key = (rows, int(transpose))
     hit = cache.get(key)
     if hit is not None and hit[0] == w._version and hit[2] == w.data_ptr():
         return hit[1]
     lib = _lib.load()
-    n_rows, k = (w2.shape[1], rows) if transpose else (rows, w2.shape[1])
+    n_rows, k = (w2.shape[1], rows) if int(transpose) == 1 else (rows, w2.shape[1])
     buf = hit[1] if hit is not None else torch.empty(int(lib.cgat_packed_floats(n_rows, k)), dtype=torch.float32,
                                                      device=w.device)
     _lib.call("cgat_pack_kmajor", _lib.ptr(w2), w2.stride(0), n_rows, k, int(transpose), _lib.ptr(buf),
@@ -165,7 +182,7 @@ class _HyperLinear(torch.autograd.Function):
     tensor never materialised in forward (cgat_hyper_rowdot_fwd)."""
 
     @staticmethod
-    def forward(ctx, z, weight, bias, y, w_packed):
+    def forward(ctx, z, weight, bias, y, w_packed, w_packed_bt):
         z, y = _f32c(z), _f32c(y)
         n, f = y.shape
         ff = f * f
@@ -177,23 +194,45 @@ class _HyperLinear(torch.autograd.Function):
                   _lib.ptr(out), n, f, _lib.stream(),
                   work=dict(key="hyper_rowdot_fwd", bound="tensor", flops=2.0 * n * f * ff,
                             note="3xTF32: 3 tensor passes per algorithmic flop"))
-        ctx.save_for_backward(z, weight, bias, y)
+        ctx.save_for_backward(z, weight, bias, y, w_packed, w_packed_bt)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        # recompute the predicted weights (library GEMM path for now; fused backward kernels replace this)
-        z, weight, bias, y = ctx.saved_tensors
+        z, weight, bias, y, w_packed, w_packed_bt = ctx.saved_tensors
         n, f = y.shape
         ff = f * f
-        g = g.contiguous()
-        p_w = torch.addmm(bias[:ff], z, weight[:ff].t()).view(n, f, f)          # (N, out, in)
-        g_y = torch.bmm(g.unsqueeze(1), p_w).squeeze(1)
-        g_p = torch.cat([(g.unsqueeze(2) * y.unsqueeze(1)).reshape(n, ff), g], dim=1)
-        g_z = g_p @ weight
-        g_w = g_p.t() @ z
-        g_b = g_p.sum(dim=0)
-        return g_z, g_w, g_b, g_y, None
+        g = _f32c(g)
+        parts = int(_lib.load().cgat_hyper_rowscale_parts(n, f))
+        work = dict(key="hyper_rowscale", bound="tensor", flops=2.0 * n * f * ff,
+                    note="3xTF32: 3 tensor passes per algorithmic flop")
+        # dL/dy[n,i] = sum_o g[n,o] (W z[n] + b)[o*F+i]: recomputed tile by tile on the tensor cores
+        buf = torch.empty((parts, n, f), dtype=torch.float32, device=y.device)
+        _lib.call("cgat_hyper_rowscale", _lib.ptr(z), _lib.ptr(g), _lib.ptr(w_packed), _lib.ptr(buf), n, f,
+                  _lib.stream(), work=work)
+        g_y = buf.sum(dim=0) + gemm3x(g, bias[:ff].view(f, f).t().contiguous())
+        # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ bias rows)
+        buf2 = torch.empty_like(buf)
+        _lib.call("cgat_hyper_rowscale", _lib.ptr(y), _lib.ptr(g), _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
+                  _lib.stream(), work=work)
+        g_z = buf2.sum(dim=0) + gemm3x(g, weight[ff:].t().contiguous())
+        # weight gradient: dW[o*F+i,k] = sum_n g[n,o] y[n,i] z[n,k] — contraction over atoms, outer product on the fly
+        lib = _lib.load()
+        splits = int(lib.cgat_hyper_wgrad_splits(n))
+        wpart = torch.empty((splits, ff, f), dtype=torch.float32, device=y.device)
+        _lib.call("cgat_hyper_wgrad", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(wpart), n, f, _lib.stream(),
+                  work=dict(key="hyper_wgrad", bound="tensor", flops=2.0 * n * f * ff,
+                            note="3xTF32: 3 tensor passes per algorithmic flop"))
+        g_w = torch.empty_like(weight)
+        if splits == 1:
+            g_w[:ff] = wpart[0]
+        else:
+            torch.sum(wpart, dim=0, out=g_w[:ff])
+        yz = torch.cat([y, z], dim=1)                      # bias-shaped rows: g^T [y | z]
+        gyz = gemm3x_tn(g, yz, 1)                          # (F, 2F)
+        g_w[ff:] = gyz[:, f:]
+        g_b = torch.cat([gyz[:, :f].reshape(ff), g.sum(dim=0)])
+        return g_z, g_w, g_b, g_y, None, None
 
 
 def hyper_linear(z, weight, bias, y, out_ch):
@@ -201,21 +240,36 @@ def hyper_linear(z, weight, bias, y, out_ch):
     (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209)."""
     in_ch = y.shape[1]
     if _FUSED and z.is_cuda and in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
-        return _HyperLinear.apply(z, weight, bias, y, packed_kmajor(weight, in_ch * out_ch))
+        return _HyperLinear.apply(z, weight, bias, y, packed_kmajor(weight, in_ch * out_ch),
+                                  packed_kmajor(weight, in_ch * out_ch, 2) if torch.is_grad_enabled() else None)
     p = torch.addmm(bias, z, weight.t())                            # (N, out*in + out)
     w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
     b = p[:, in_ch * out_ch:]
     return torch.baddbmm(b.unsqueeze(2), w, y.unsqueeze(2)).squeeze(2)
 
 
+def _w2_transposed_packed(w2, heads):
+    """Packed W2^T per head, (H*Hd, F): row h*Hd+k, col c = W2[h*F+c, k] — the A operand of the dgrad MMAs."""
+    cache = w2.__dict__.setdefault("_cgat_packed", {})
+    hit = cache.get("w2t")
+    if hit is not None and hit[0] == w2._version and hit[2] == w2.data_ptr():
+        return hit[1]
+    hf, hd = w2.shape[0], w2.shape[1]
+    wt = w2.detach().view(heads, hf // heads, hd).transpose(1, 2).reshape(heads * hd, hf // heads).contiguous()
+    buf = packed_kmajor(wt).clone() if hit is None else hit[1].copy_(packed_kmajor(wt))
+    cache["w2t"] = (w2._version, buf, w2.data_ptr())
+    return buf
+
+
 class _EdgeAttentionFused(torch.autograd.Function):
     """Forward: per-atom / per-rank first-layer projections (cgat_gemm3x_nt) + the fused gather /
     second-layer MMA / segmented-softmax kernel (cgat_edge_attn_fwd).  No per-edge tensor is written.
-    Backward (for now): recompute through the unfused formulation under autograd."""
+    Backward: cgat_edge_attn_bwd_prep (per-edge dL/da, dL/dv + sign masks), two cgat_edge_attn_dgrad passes
+    (edges grouped by destination / by source), cgat_edge_attn_wgrad, and the first-layer products on
+    cgat_gemm3x_nt / cgat_gemm3x_tn.  Deterministic, atomic-free."""
 
     @staticmethod
-    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads,
-                keep_stats):
+    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads):
         x, edge_table = _f32c(x), _f32c(edge_table)
         n, f = x.shape
         fe = edge_table.shape[1]
@@ -226,37 +280,83 @@ class _EdgeAttentionFused(torch.autograd.Function):
         w_rank = torch.cat([w1a2[:, f:f + fe], w1m2[:, f:f + fe]], dim=0)                           # (2*HHd, Fe)
         P = gemm3x(x, w_atom)                                                                        # (N, 4*HHd)
         T = gemm3x(edge_table, w_rank, torch.cat([b1a, b1m]))                                        # (K+1, 2*HHd)
+        train = any(ctx.needs_input_grad)
         out = torch.empty((n, heads, f), dtype=torch.float32, device=x.device)
-        smax = torch.empty_like(out) if keep_stats else None
-        sden = torch.empty_like(out) if keep_stats else None
+        smax = torch.empty_like(out) if train else None
+        sden = torch.empty_like(out) if train else None
         e = plan.n_edges
+        b2a, b2m = b2a.contiguous(), b2m.contiguous()
         _lib.call("cgat_edge_attn_fwd", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed),
-                  _lib.ptr(b2a.contiguous()), _lib.ptr(b2m.contiguous()), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden),
+                  _lib.ptr(b2a), _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden),
                   n, e, heads, f, hd, 1e-16, _lib.stream(),
                   work=dict(key="edge_attn_fwd", bound="tensor", flops=2.0 * e * heads * hd * 2 * f,
                             bytes=4.0 * (e * (3 + 2 * 2 * hhd) + n * heads * f),
                             note="second MLP layer (E x Hd x F per head, gate+message) on tcgen05, 3xTF32"))
-        ctx.save_for_backward(x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m)
-        ctx.plan, ctx.heads = plan, heads
+        if train:
+            ctx.save_for_backward(x, edge_table, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax,
+                                  sden, w_atom, w_rank)
+            ctx.plan, ctx.heads = plan, heads
         return out
 
     @staticmethod
     def backward(ctx, g):
-        saved = ctx.saved_tensors
-        need = ctx.needs_input_grad[:10]
-        with torch.enable_grad():
-            ins = [t.detach().requires_grad_(nd) for t, nd in zip(saved, need)]
-            x, tab, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m = ins
-            hhd = w1a.shape[0]
-            heads = ctx.heads
-            agg = edge_attention_heads_unfused(x, tab, ctx.plan, w1a.view(hhd, -1), b1a,
-                                               w2a.view(heads, -1, hhd // heads), b2a, w1m.view(hhd, -1), b1m,
-                                               w2m.view(heads, -1, hhd // heads), b2m, heads)
-            req = [t for t, nd in zip(ins, need) if nd]
-            grads = torch.autograd.grad(agg, req, g)
-        it = iter(grads)
-        return tuple(next(it) if nd else None for nd in need) + (None,) * 5
+        (x, tab, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax, sden, w_atom,
+         w_rank) = ctx.saved_tensors
+        plan, heads = ctx.plan, ctx.heads
+        n, f = x.shape
+        fe = tab.shape[1]
+        hhd = w1a.shape[0]
+        hd = hhd // heads
+        e = plan.n_edges
+        kcn = (hd + 31) // 32
+        dev = x.device
+        lib = _lib.load()
+        g = _f32c(g)
+        st = _lib.stream()
+        # 1. per-edge dL/da, dL/dv and LeakyReLU sign masks
+        d_gate = torch.empty((e, heads, f), dtype=torch.float32, device=dev)
+        d_msg = torch.empty_like(d_gate)
+        signs = torch.empty(2 * heads * kcn * max(e, 1), dtype=torch.int32, device=dev)
+        flops2 = 2.0 * e * heads * hd * 2 * f
+        _lib.call("cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
+                  _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed), _lib.ptr(b2a),
+                  _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(g), _lib.ptr(d_gate),
+                  _lib.ptr(d_msg), _lib.ptr(signs), n, e, heads, f, hd, 1e-16, st,
+                  work=dict(key="edge_attn_bwd_prep", bound="tensor", flops=flops2))
+        # 2. dgrad + segment sums, edges grouped by destination then by source
+        d_p = torch.zeros((n, 4 * hhd), dtype=torch.float32, device=dev)
+        wt_a, wt_m = _w2_transposed_packed(w2a, heads), _w2_transposed_packed(w2m, heads)
+        n_ranks = tab.shape[0]
+        grid = int(lib.cgat_edge_attn_dgrad_grid(e))
+        d_rank = torch.zeros((grid, n_ranks, 2 * hhd), dtype=torch.float32, device=dev)
+        wk = dict(key="edge_attn_dgrad", bound="tensor", flops=flops2)
+        _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(plan.rowptr),
+                  _lib.ptr(plan.dst), None, None, _lib.ptr(wt_a), _lib.ptr(wt_m), _lib.ptr(d_p), 4 * hhd, 0, None,
+                  n_ranks, n, e, heads, f, hd, st, work=wk)
+        so = plan.by_source()
+        _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(so.rowptr),
+                  _lib.ptr(so.seg), _lib.ptr(so.row), _lib.ptr(so.rank), _lib.ptr(wt_a), _lib.ptr(wt_m), _lib.ptr(d_p),
+                  4 * hhd, 2 * hhd, _lib.ptr(d_rank), n_ranks, n, e, heads, f, hd, st, work=wk)
+        d_t = d_rank.sum(dim=0)                                                     # (K+1, 2*HHd)
+        # 3. second-layer weight / bias gradients
+        splits = int(lib.cgat_edge_attn_wgrad_splits(heads))
+        part = torch.empty((splits, 2, heads, f, hd), dtype=torch.float32, device=dev)
+        _lib.call("cgat_edge_attn_wgrad", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
+                  _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(part), e, heads, f, hd, st,
+                  work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2))
+        d_w2 = part.sum(dim=0)
+        g_w2a, g_w2m = d_w2[0].reshape(w2a.shape), d_w2[1].reshape(w2m.shape)
+        g_b2a, g_b2m = d_gate.sum(dim=0).reshape(-1), d_msg.sum(dim=0).reshape(-1)
+        # 4. first layer: P = x w_atom^T, T = tab w_rank^T + b1
+        g_x = gemm3x(d_p, w_atom.t().contiguous())
+        g_watom = gemm3x_tn(d_p, x)                                                 # (4*HHd, F)
+        g_tab = d_t @ w_rank
+        g_wrank = d_t.t() @ tab                                                     # (2*HHd, Fe)
+        g_b1 = d_t.sum(dim=0)
+        g_w1a = torch.cat([g_watom[:hhd], g_wrank[:hhd], g_watom[2 * hhd:3 * hhd]], dim=1).reshape(w1a.shape)
+        g_w1m = torch.cat([g_watom[hhd:2 * hhd], g_wrank[hhd:], g_watom[3 * hhd:]], dim=1).reshape(w1m.shape)
+        return (g_x, g_tab, g_w1a, g_b1[:hhd], g_w2a, g_b2a, g_w1m, g_b1[hhd:], g_w2m, g_b2m, None, None, None, None)
 
 
 def edge_attention_heads_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
@@ -285,13 +385,14 @@ def edge_attention(x, edge_table, plan, mh_a, mh_m, heads):
     the gate / message MultiHeadNetwork modules (parameters fc_in/fc_out in the reference's Conv1d layout)."""
     f = x.shape[1]
     hd = mh_a.hidden_dim
-    fused_ok = (_FUSED and x.is_cuda and f == 128 and mh_a.output_dim == f and mh_m.output_dim == f and hd % 4 == 0
-                and heads <= 8 and edge_table.shape[1] % 4 == 0)
+    fused_ok = (_FUSED and x.is_cuda and f == 128 and mh_a.output_dim == f and mh_m.output_dim == f
+                and hd % 128 == 0 and hd <= 256 and heads <= 8 and edge_table.shape[1] % 4 == 0
+                and edge_table.shape[0] <= 32)
     if fused_ok:
         out = _EdgeAttentionFused.apply(x, edge_table, mh_a.fc_in.weight, mh_a.fc_in.bias, mh_a.fc_out.weight,
                                         mh_a.fc_out.bias, mh_m.fc_in.weight, mh_m.fc_in.bias, mh_m.fc_out.weight,
                                         mh_m.fc_out.bias, packed_kmajor(mh_a.fc_out.weight),
-                                        packed_kmajor(mh_m.fc_out.weight), plan, heads, False)
+                                        packed_kmajor(mh_m.fc_out.weight), plan, heads)
         return out.mean(dim=1)
     return edge_attention_unfused(x, edge_table, plan, mh_a.w_in(), mh_a.fc_in.bias, mh_a.w_out(), mh_a.fc_out.bias,
                                   mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads)

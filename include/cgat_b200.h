@@ -77,8 +77,15 @@ int cgat_seg_softmax_bwd(const float* gate, const float* value, const float* u, 
 int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act, void* stream);
 
+/* C[s][M,N] = sum_{k in split s} A[k,m] * B[k,n]  (A [K x M], B [K x N] row-major): the weight-gradient
+ * shape dW = dY^T X of every nn.Linear / Conv1d(k=1) backward on this path.  Operands are staged
+ * MN-major (no transposed copies).  n_split partial results `split_stride` floats apart.          */
+int cgat_gemm3x_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                   int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split, void* stream);
+
 /* ---- packed tensor-core operands ---------------------------------------------------------------
- * fp32 [rows x k] (or its transpose, transpose=1: stored [k x rows]) -> 128-row x 32-float tiles,
+ * fp32 [rows x k] (transpose=1: given as [k x rows]; transpose=2: each 128x128 block transposed)
+ * -> 128-row x 32-float tiles,
  * pre-split into (tf32 hi, tf32 lo) and pre-swizzled; layout [row_tile][k_chunk][hi|lo][16 KB].
  * `out` holds cgat_packed_floats(rows,k) floats.  Repack after every weight update.              */
 int64_t cgat_packed_floats(int64_t rows, int64_t k);
@@ -107,6 +114,50 @@ int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, co
                        const float* w2m_packed, const float* b2a, const float* b2m, float* out,
                        float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
                        int32_t f, int32_t hd, float eps, void* stream);
+
+/* Backward companion of cgat_hyper_rowdot_fwd (activation gradients):
+ *   partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m]);  result = sum_c partial[c]
+ * (a = z, blocks of W)            -> dL/dy_in[n,i] = sum_o g[n,o] * (W z + ..)[o,i]
+ * (a = y, transposed blocks of W) -> dL/dz[n,k]    = sum_o g[n,o] * sum_i y[n,i] W[o*F+i,k]
+ * partial holds cgat_hyper_rowscale_parts(n_atoms, f) x n_atoms x f floats.                      */
+int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f);
+int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_packed, float* partial,
+                        int64_t n_atoms, int32_t f, void* stream);
+
+/* Weight gradient of the hyper-linear layer: dL/dW[o*F+i, k] = sum_n g[n,o] y[n,i] z[n,k], contracted over
+ * atoms with MN-major operands; the scaled rows g[n,o]*y[n,:] are formed while staging (the reference's
+ * autograd materialises the (N, F*F) gradient of the predicted weights instead).
+ * out: (cgat_hyper_wgrad_splits(N), F*F, F) partial results; sum over dim 0.                       */
+int32_t cgat_hyper_wgrad_splits(int64_t n_atoms);
+int cgat_hyper_wgrad(const float* g, const float* y, const float* z, float* out, int64_t n_atoms, int32_t f,
+                     void* stream);
+
+/* ---- fused edge attention, backward -------------------------------------
+ * Step 1: recompute a, v; write d_gate = dL/da, d_msg = dL/dv (E,H,F; destination-sorted rows) and the
+ *         LeakyReLU sign masks signs[2][H][ceil(Hd/32)][E].  g_out = dL/d out (N,H,F).
+ * Step 2 (run once per edge grouping: by destination, by source): d_hid = dZ W2 on the tensor cores,
+ *         d_pre = d_hid * leaky_relu'(pre), G[seg, col_off + ...] = per-segment sums (= dL/dP blocks), and
+ *         optionally per-rank partial sums d_rank (grid, n_ranks, 2*H*Hd) (= dL/dT after summing dim 0).
+ *         wt_*_packed: cgat_pack_kmajor of W2^T per head, shape (H*Hd, F).
+ * Step 3: dL/dW2 = dZ^T hid, contraction over edges with MN-major operands; partial results
+ *         (cgat_edge_attn_wgrad_splits(H), 2, H, F, Hd).
+ * Together they replace autograd through index_select / grouped Conv1d / softmax / scatter_add.     */
+int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                            const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                            const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
+                            const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
+                            float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                            int32_t f, int32_t hd, float eps, void* stream);
+int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges);
+int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t* signs, const int32_t* segptr,
+                         const int32_t* seg, const int32_t* row, const int32_t* rnk, const float* wt_a_packed,
+                         const float* wt_m_packed, float* G, int64_t ldg, int32_t col_off, float* d_rank,
+                         int32_t n_ranks, int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd,
+                         void* stream);
+int32_t cgat_edge_attn_wgrad_splits(int32_t heads);
+int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
+                         const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
+                         int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream);
 
 #ifdef __cplusplus
 }

@@ -56,3 +56,19 @@ def test_gemm3x_strided_operands():
     c = gemm(a, b)
     bound = a.double().abs() @ b.double().abs().t()
     assert ((c.double() - a.double() @ b.double().t()).abs() / bound).max().item() < 2e-6
+
+
+@pytest.mark.parametrize("K,M,N,split", [(32, 128, 128, 1), (8, 128, 128, 1), (100, 128, 128, 1), (5000, 256, 128, 1),
+                                         (5559, 200, 132, 4), (66000, 128, 256, None), (700, 5120, 128, None)])
+def test_gemm3x_tn_matches_fp64(K, M, N, split):
+    """cgat_gemm3x_tn (MN-major UMMA operands): a.T @ b, the weight-gradient shape."""
+    from cgat_b200 import ops
+    g = torch.Generator().manual_seed(K + M + N)
+    a = torch.randn(K, M, generator=g).to(DEV)
+    b = torch.randn(K, N, generator=g).to(DEV)
+    c = ops.gemm3x_tn(a, b, split)
+    ref = a.double().t() @ b.double()
+    bound = a.double().abs().t() @ b.double().abs()
+    rel = ((c.double() - ref).abs() / bound).max().item()
+    print(f"gemm3x_tn {K}x{M}x{N}: max err / sum|a||b| = {rel:.3e}")
+    assert rel <= 3e-7 + 2e-7 * (K / 8) ** 0.5, f"max err / sum|a||b| = {rel:.3e}"

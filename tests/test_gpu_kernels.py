@@ -189,4 +189,66 @@ def test_edge_attention_fused_matches_oracle(n_cry, k, heads, lo, hi):
     w = torch.randn(n, f, generator=torch.Generator().manual_seed(5)).double()
     (refg * w).sum().backward()
     (out * w.float().to(DEV)).sum().backward()
-    assert_close(xc.grad, xd.grad, "edge attention d_x", atol=1e-4, rtol=1e-3)
+    from tests._cases import assert_grad_close
+    assert_grad_close(xc.grad, xd.grad, "edge attention d_x")
+
+
+@pytest.mark.parametrize("n_cry,k,heads,lo,hi", [(3, 12, 5, 2, 20), (60, 12, 5, 2, 20), (2, 24, 2, 200, 256),
+                                                 (500, 12, 5, 2, 20)])
+def test_edge_attention_fused_backward_all_grads(n_cry, k, heads, lo, hi):
+    """Fused edge-attention backward (bwd_prep + dgrad x2 + wgrad + first-layer GEMMs): every gradient
+    against autograd through the fp64 restatement of GATConvNodes.message/aggregate."""
+    from cgat_b200.CGAT import MultiHeadNetwork
+    from tests._cases import assert_grad_close
+    f, fe = 128, 128
+    sb = synthetic.make_batch(n_cry, k, seed=100 + n_cry, atoms_lo=lo, atoms_hi=hi)
+    gidx = sb.graph
+    n = gidx.num_nodes
+    torch.manual_seed(n_cry)
+    width = 2 * f + fe
+    mh_a = MultiHeadNetwork(width, f, int(width / 1.5), heads)
+    mh_m = MultiHeadNetwork(width, f, int(width / 1.5), heads)
+    x = torch.randn(n, f) * 0.5
+    tab = torch.randn(k + 1, fe)
+    w = torch.randn(n, f, generator=torch.Generator().manual_seed(5))
+    # fp64 oracle with autograd
+    sd = {}
+    for pre, mod in (("A.", mh_a), ("M.", mh_m)):
+        for kk, v in mod.state_dict().items():
+            sd[pre + kk] = v.double().requires_grad_(True)
+    xd, tabd = x.double().requires_grad_(True), tab.double().requires_grad_(True)
+    src, dst = gidx.edge_index
+    m = torch.cat([xd[dst], tabd[gidx.edge_attr], xd[src]], dim=1)
+    alpha = O.pyg_softmax(O.multi_head_network(sd, "A.", m, heads), dst, n)
+    ref = O.seg_sum(O.multi_head_network(sd, "M.", m, heads) * alpha, dst, n).mean(dim=1)
+    (ref * w.double()).sum().backward()
+    # fused
+    plan = graph.build_edge_plan(gidx.edge_index.to(DEV), gidx.edge_attr.to(DEV), n)
+    mh_a, mh_m = mh_a.to(DEV), mh_m.to(DEV)
+    xc, tabc = x.to(DEV).requires_grad_(True), tab.to(DEV).requires_grad_(True)
+    out = ops.edge_attention(xc, tabc, plan, mh_a, mh_m, heads)
+    (out * w.to(DEV)).sum().backward()
+    assert_close(out.detach(), ref.detach(), "fwd", atol=2e-5, rtol=1e-4)
+    assert_grad_close(xc.grad, xd.grad, "d_x")
+    # d_table sums E * 2*H*Hd signed terms per entry (heavy cancellation): calibrate the fp32 noise floor with the
+    # library-GEMM formulation of the same op and require the fused path to sit at that floor
+    xu, tabu = x.to(DEV).requires_grad_(True), tab.to(DEV).requires_grad_(True)
+    outu = ops.edge_attention_unfused(xu, tabu, plan, mh_a.w_in(), mh_a.fc_in.bias, mh_a.w_out(), mh_a.fc_out.bias,
+                                      mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads)
+    (gu_x, gu_tab) = torch.autograd.grad((outu * w.to(DEV)).sum(), [xu, tabu])
+    floor = (gu_tab.cpu().double() - tabd.grad).abs().max().item()
+    err = (tabc.grad.cpu().double() - tabd.grad).abs().max().item()
+    print(f"d_table: fused err {err:.3e}, library-fp32 err {floor:.3e}, ref max {tabd.grad.abs().max().item():.3e}")
+    assert err <= max(4 * floor, 1e-4 + 1e-3 * tabd.grad.abs().max().item() * 0.1), (err, floor)
+    for pre, mod in (("A.", mh_a), ("M.", mh_m)):
+        for kk, p in mod.named_parameters():
+            ref_g = sd[pre + kk].grad
+            scale = max(ref_g.abs().max().item(), 1e-3)
+            assert_grad_close(p.grad, ref_g, f"d_{pre}{kk}", atol=1e-4 + 1e-5 * scale)
+    # deterministic
+    xc2 = x.to(DEV).requires_grad_(True)
+    for p in list(mh_a.parameters()) + list(mh_m.parameters()):
+        p.grad = None
+    out2 = ops.edge_attention(xc2, tabc, plan, mh_a, mh_m, heads)
+    (out2 * w.to(DEV)).sum().backward()
+    assert torch.equal(xc2.grad, xc.grad), "fused backward is not deterministic"
