@@ -27,7 +27,8 @@ constexpr int kBThreads = 128 + kBProducers + 32;
 constexpr int kBStages = 3;
 constexpr int kBStageBytes = 2 * (int)kPackStageBytes;
 constexpr int kBMetaBufs = 4;
-constexpr int kBMetaBytes = kBMetaBufs * 3 * kBT * 4;
+constexpr int kBMetaStride = 3 * kBT + 8;  // seg | row | rank | 4 words of segment-start flags | 4 words of rank-run flags
+constexpr int kBMetaBytes = kBMetaBufs * kBMetaStride * 4;
 constexpr int kBMaxRanks = 32;
 constexpr int kBRankBytes = kBMaxRanks * 128 * 4;
 constexpr int kBSmemBytes = kBStages * kBStageBytes + kBMetaBytes + kBRankBytes + 256 + 1024;
@@ -64,7 +65,7 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
-  int32_t* meta = reinterpret_cast<int32_t*>(smem + kBStages * kBStageBytes);  // [4][seg|row|rank][128]
+  int32_t* meta = reinterpret_cast<int32_t*>(smem + kBStages * kBStageBytes);  // [4][seg|row|rank|flags]
   float* rank_acc = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(meta) + kBMetaBytes);  // [n_ranks][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(rank_acc) + kBRankBytes);
   uint64_t* full = bars;
@@ -110,6 +111,9 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
 
   if (warp < 4) {
     // ---------------------------------------------------------------- epilogue
+    // Thread = hidden unit (TMEM lane).  Per edge column: one FADD for hi+lo, a select for the LeakyReLU slope and
+    // one FADD into the running segment sum; segment / rank-run boundaries come as precomputed bit masks so the
+    // common path is branch-free (boundaries are ~1 in max_nbr columns).
     const int c = warp * 32 + lane;
     const uint32_t bitpos = (uint32_t)((lane & 3) * 8 + (lane >> 2));
     uint32_t icount = 0;
@@ -119,56 +123,85 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
       const bool kvalid = kk < hd;
       const int col = net * hhd + h * hd + kk;
       const uint32_t* sg = g.signs + ((int64_t)(net * H + h) * kcn + (half * 4 + warp)) * g.n_edges;
+      float* gcol = g.G + g.col_off + col;
       float acc = 0.f, racc = 0.f;
       int cur = -1, currk = -1;
       for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
         const int e0 = e_lo + tile * kBT;
         const int nv = min(kBT, e_hi - e0);
-        const int32_t* mt = meta + (icount & (kBMetaBufs - 1)) * 3 * kBT;
+        const int32_t* mt = meta + (icount & (kBMetaBufs - 1)) * kBMetaStride;
         const uint32_t b = icount & 1u;
         mbar_wait(&tmem_full[b], (icount >> 1) & 1u);
         tc_fence_after();
+        // tile start: the only place where "same segment as before?" needs a compare (once per tile)
+        {
+          const int sid0 = mt[0];
+          if (sid0 != cur) {
+            if (cur >= 0 && kvalid) gcol[(int64_t)cur * g.ldg] = acc;
+            acc = 0.f, cur = sid0;
+          }
+          const int rk0 = mt[2 * kBT];
+          if (g.d_rank && rk0 != currk) {
+            if (currk >= 0) rank_acc[currk * 128 + c] += racc;
+            racc = 0.f, currk = rk0;
+          }
+        }
         const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + b * 256;
 #pragma unroll 1
         for (int cc = 0; cc < kBT / 32; ++cc) {
-          // sign words of these 32 edges first: 32 independent loads in flight (the stores to G below would
-          // otherwise serialise them one column at a time)
+          // LeakyReLU sides of these 32 edges: all loads issued before anything else
           uint32_t wd[32];
+          if (g.row == nullptr) {
+            const uint4* sp = reinterpret_cast<const uint4*>(sg + e0 + cc * 32);
+            const bool aligned = ((reinterpret_cast<uintptr_t>(sp) & 15) == 0) && (cc * 32 + 32 <= nv);
+            if (aligned) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int t = cc * 32 + j;
-            wd[j] = (kvalid && t < nv) ? __ldg(sg + mt[kBT + t]) : 0u;
+              for (int j = 0; j < 8; ++j) {
+                const uint4 q = kvalid ? __ldg(sp + j) : make_uint4(0, 0, 0, 0);
+                wd[4 * j] = q.x, wd[4 * j + 1] = q.y, wd[4 * j + 2] = q.z, wd[4 * j + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) wd[j] = (kvalid && cc * 32 + j < nv) ? __ldg(sg + e0 + cc * 32 + j) : 0u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) wd[j] = (kvalid && cc * 32 + j < nv) ? __ldg(sg + mt[kBT + cc * 32 + j]) : 0u;
           }
+          // bit j: edge cc*32+j starts a new segment / rank run (never set for the first edge of the tile and for
+          // the padding columns, whose accumulator entries are exactly 0)
+          const uint32_t segflags = (uint32_t)mt[3 * kBT + cc];
+          const uint32_t rnkflags = g.d_rank ? (uint32_t)mt[3 * kBT + 4 + cc] : 0u;
           float v[32], w[32];
           tmem_ld32(tbase + cc * 32, v);
           tmem_ld32(tbase + 128 + cc * 32, w);
           tmem_ld_wait();
+          // branch-free common path: the flush is one predicated store to a pointer kept ready, the rest selects
+          float* gp = gcol + (int64_t)cur * g.ldg;
+          float* rp = rank_acc + max(currk, 0) * 128 + c;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const int t = cc * 32 + j;
-            if (t < nv) {
-              const int sid = mt[t];
-              const float dp = (v[j] + w[j]) * (((wd[j] >> bitpos) & 1u) ? 1.f : 0.01f);
-              if (sid != cur) {
-                if (cur >= 0 && kvalid) g.G[(int64_t)cur * g.ldg + g.col_off + col] = acc;
-                acc = 0.f, cur = sid;
-              }
-              acc += dp;
-              if (g.d_rank) {
-                const int rk = mt[2 * kBT + t];
-                if (rk != currk) {
-                  if (currk >= 0) rank_acc[currk * 128 + c] += racc;
-                  racc = 0.f, currk = rk;
-                }
-                racc += dp;
-              }
+            const bool sf = ((segflags >> j) & 1u) && kvalid;
+            if (sf) *gp = acc;
+            acc = ((segflags >> j) & 1u) ? 0.f : acc;
+            gp = gcol + (int64_t)mt[cc * 32 + j] * g.ldg;
+            if (g.d_rank) {
+              const bool rf = (rnkflags >> j) & 1u;
+              if (rf) *rp += racc;
+              racc = rf ? 0.f : racc;
+              rp = rank_acc + mt[2 * kBT + cc * 32 + j] * 128 + c;
             }
+            const float dp = (v[j] + w[j]) * (((wd[j] >> bitpos) & 1u) ? 1.f : 0.01f);
+            acc += dp;
+            racc += dp;
           }
+          cur = mt[cc * 32 + 31];
+          currk = mt[2 * kBT + cc * 32 + 31];
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[b]);
       }
-      if (cur >= 0 && kvalid) g.G[(int64_t)cur * g.ldg + g.col_off + col] = acc;
+      if (cur >= 0 && kvalid) gcol[(int64_t)cur * g.ldg] = acc;
       if (g.d_rank) {
         if (currk >= 0) rank_acc[currk * 128 + c] += racc;
         float* dst = g.d_rank + (int64_t)blockIdx.x * g.n_ranks * 2 * hhd + col;
@@ -189,19 +222,27 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
       for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
         const int e0 = e_lo + tile * kBT;
         const int nv = min(kBT, e_hi - e0);
-        int32_t* mt = meta + (icount & (kBMetaBufs - 1)) * 3 * kBT;
+        int32_t* mt = meta + (icount & (kBMetaBufs - 1)) * kBMetaStride;
         if (pt < kBT) {
           const bool ok = pt < nv;
-          mt[pt] = ok ? g.seg[e0 + pt] : -1;
-          mt[kBT + pt] = ok ? (g.row ? g.row[e0 + pt] : e0 + pt) : 0;
-          mt[2 * kBT + pt] = (ok && g.rnk) ? g.rnk[e0 + pt] : 0;
+          const int e = e0 + (ok ? pt : nv - 1);  // padding columns repeat the last valid edge's ids (their data is 0)
+          const int sid = g.seg[e];
+          const int rk = g.rnk ? g.rnk[e] : 0;
+          mt[pt] = sid;
+          mt[kBT + pt] = ok ? (g.row ? g.row[e] : e) : -1;
+          mt[2 * kBT + pt] = rk;
+          // boundary flags (bit t of word t/32): segment / rank differs from the edge before (never for t = 0)
+          const bool sflag = ok && pt > 0 && g.seg[e - 1] != sid;
+          const bool rflag = ok && pt > 0 && g.rnk && g.rnk[e - 1] != rk;
+          const uint32_t sw = __ballot_sync(0xffffffffu, sflag), rw = __ballot_sync(0xffffffffu, rflag);
+          if (lane == 0) mt[3 * kBT + (pt >> 5)] = (int32_t)sw, mt[3 * kBT + 4 + (pt >> 5)] = (int32_t)rw;
         }
         asm volatile("bar.sync 1, %0;" ::"n"(kBProducers) : "memory");
         int64_t rowoff[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = (pt + kBProducers * j) >> 3;
-          rowoff[j] = (r < nv) ? ((int64_t)mt[kBT + r] * H + h) * kBF : -1;
+          rowoff[j] = (r < nv) ? ((int64_t)mt[kBT + r] * H + h) * kBF : -1;  // padding rows are staged as zeros
         }
         for (int kc = 0; kc < kcf; ++kc, ++cnt) {
           const uint32_t s = cnt % kBStages, u = cnt / kBStages;

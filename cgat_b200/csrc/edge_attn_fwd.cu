@@ -19,8 +19,8 @@
 // One persistent CTA per SM owns a contiguous range of destination atoms (hence whole softmax
 // segments), balanced by edge count.  Roles (416 threads):
 //   warps 0-3   epilogue: tcgen05.ld gate/message rows, segmented online softmax, write out[d,h,:]
-//   warps 4-11  producers: gather + LeakyReLU + split -> shared memory (B operand); thread 0 also issues the
-//               cp.async.bulk of the pre-packed W2 chunk (A operand); 3-stage full/empty mbarrier ring
+//   warps 4-11  producers: gather + LeakyReLU + split -> shared memory (B operand); the first of them also
+//               issues the cp.async.bulk of the pre-packed W2 chunk (A operand); 3-stage full/empty mbarrier ring
 //   warp  12    TMEM allocation (512 columns: 2 heads x {gate, message} x 128) + single-thread MMA issue
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -31,13 +31,16 @@ using namespace tc;
 
 constexpr int kET = 128;             // edges per tile (MMA N)
 constexpr int kEF = 128;             // output channels per head (MMA M) — instantiated for F = 128
-constexpr int kEProducers = 256;
+constexpr int kEProducers = 512;     // producer threads; kEProducers / kEGroup groups alternate pipeline stages
+constexpr int kEGroup = 256;
+constexpr int kEMmaWarp = (128 + kEProducers) / 32;
 constexpr int kEThreads = 128 + kEProducers + 32;
 constexpr int kEStages = 3;
 constexpr int kEStageBytes = 2 * (int)kPackStageBytes;  // [W2 chunk hi|lo][hidden chunk hi|lo]
 constexpr int kEMaxHeads = 8;
 constexpr int kEMetaBufs = 4;          // tile metadata ring (producers run ahead of the epilogue)
-constexpr int kEMetaBytes = kEMetaBufs * 3 * kET * 4;
+constexpr int kEMetaStride = 4 * kET + 8;  // dst | src | rank | dst*H*F | 4 words segment-start flags | 4 words valid mask
+constexpr int kEMetaBytes = kEMetaBufs * kEMetaStride * 4;
 constexpr int kECarryBytes = kEMaxHeads * 4 * kEF * 4;  // (max, den, acc, open dst) per head and channel
 constexpr int kESmemBytes = kEStages * kEStageBytes + kEMetaBytes + kECarryBytes + 256 + 1024;
 
@@ -78,6 +81,25 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 
 __device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
 
+// exp(x) for x <= 0 on the SFU with fp32-level accuracy: ex2.approx (2^-22.5 relative) on the rounded product
+// x*log2(e), times (1 + residual*ln2) where the residual carries the rounding error of that product and the low
+// bits of log2(e) — without it the error grows like |x| * 6e-8.  Inputs below -87 (incl. -inf) are clamped: the
+// result (1.6e-38) only ever multiplies zeros or is added to sums >= 1.
+__device__ __forceinline__ float fast_exp(float x) {
+  const float xc = fmaxf(x, -87.f);
+  const float t = xc * 1.4426950216293335f;
+  float lo = fmaf(xc, 1.4426950216293335f, -t);
+  lo = fmaf(xc, 1.9259629911266175e-8f, lo);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+  return fmaf(e, lo * 0.6931471805599453f, e);
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+
 // kMode 0: forward (segmented online softmax, writes out / max / den)
 // kMode 1: backward-prep: recompute a, v and emit  d_msg = alpha * g,  d_gate = alpha * (v - out) * g  per edge
 //          (alpha from the saved per-segment max / den) plus the sign masks of the hidden pre-activations.
@@ -86,7 +108,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
-  int32_t* meta = reinterpret_cast<int32_t*>(smem + kEStages * kEStageBytes);          // [4][3][128]
+  int32_t* meta = reinterpret_cast<int32_t*>(smem + kEStages * kEStageBytes);          // [4][dst|src|rank|off|flags|valid]
   float* carry = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(meta) + kEMetaBytes);  // [H][4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(carry) + kECarryBytes);
   uint64_t* full = bars;                        // [3]
@@ -102,7 +124,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
 
   if (tid == 0) {
     for (int s = 0; s < kEStages; ++s) {
-      mbar_init(&full[s], kEProducers);
+      mbar_init(&full[s], kEGroup);
       mbar_init(&empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     range[0] = g.rowptr[a_lo];
     range[1] = g.rowptr[a_hi];
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == kEMmaWarp) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -128,115 +150,153 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
 
   if (warp < 4) {
     // ---------------------------------------------------------------- epilogue
-    const int c = warp * 32 + lane;  // channel = TMEM lane
+    // Thread = channel (TMEM lane); it walks the tile's 128 edge columns.  Segment boundaries arrive as bit masks
+    // from the producers, so the per-column code is straight-line: the flush of a finished segment is a predicated
+    // store to an address kept ready, resets are selects, exp runs on the SFU (fast_exp).
+    const int c = warp * 32 + lane;
+    const int hf = H * kEF;
     uint32_t hcount = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int e0 = e_lo + tile * kET;
       const int nv = min(kET, e_hi - e0);
-      const int32_t* mdst = meta + (tile & (kEMetaBufs - 1)) * 3 * kET;
+      const int32_t* mt = meta + (tile & (kEMetaBufs - 1)) * kEMetaStride;
       const bool last_tile = (tile == n_tiles - 1);
       for (int h = 0; h < H; ++h, ++hcount) {
         const uint32_t hb = hcount & 1u;
         float* cs = carry + (h * 4) * kEF;
-        float m = -INFINITY, den = 0.f, acc = 0.f;  // kMode 1 reuses them as (seg max, 1/(den+eps), out) of the open segment
-        float gg = 0.f;
-        int d = -1;
-        if (kMode == 0 && tile > 0) {
-          m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = __float_as_int(cs[3 * kEF + c]);
-        }
-        const float ba = __ldg(g.b2a + h * kEF + c), bm = __ldg(g.b2m + h * kEF + c);
+        const int hc = h * kEF + c;
+        const float ba = __ldg(g.b2a + hc), bm = __ldg(g.b2m + hc);
         mbar_wait(&tmem_full[hb], (hcount >> 1) & 1u);
         tc_fence_after();
         const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + hb * 256;
-#pragma unroll 1
-        for (int cc = 0; cc < kET / 32; ++cc) {
-          float av[32], vv[32];
-          tmem_ld32(tbase + cc * 32, av);
-          tmem_ld32(tbase + 128 + cc * 32, vv);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int t = cc * 32 + j;
-            if (t < nv) {
-              const int dc = mdst[t];
-              const float a = av[j] + ba, v = vv[j] + bm;
-              if (kMode == 0) {
-                if (dc != d) {
-                  if (d >= 0) {
-                    const int64_t o = ((int64_t)d * H + h) * kEF + c;
-                    g.out[o] = acc / (den + g.eps);
-                    if (g.smax) g.smax[o] = m, g.sden[o] = den;
-                  }
-                  m = -INFINITY, den = 0.f, acc = 0.f, d = dc;
-                }
-                const float mn = fmaxf(m, a);
-                const float r = expf(m - mn), p = expf(a - mn);
-                den = den * r + p;
-                acc = acc * r + p * v;
-                m = mn;
-              } else {
-                if (dc != d) {
-                  const int64_t o = ((int64_t)dc * H + h) * kEF + c;
-                  m = __ldg(g.smax + o);
-                  den = 1.f / (__ldg(g.sden + o) + g.eps);
-                  acc = __ldg(g.out + o);
-                  gg = __ldg(g.g_out + o);
-                  d = dc;
-                }
-                const float alpha = expf(a - m) * den;
-                const int64_t o = ((int64_t)(e0 + t) * H + h) * kEF + c;
-                g.d_msg[o] = alpha * gg;
-                g.d_gate[o] = alpha * (v - acc) * gg;
+        if (kMode == 0) {
+          float m = -INFINITY, den = 0.f, acc = 0.f;
+          int d = -1;
+          if (tile > 0) m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = __float_as_int(cs[3 * kEF + c]);
+          {  // tile start: the one place that needs a compare against the carried segment
+            const int d0 = mt[0];
+            if (d0 != d) {
+              if (d >= 0) {
+                const int64_t o = (int64_t)d * hf + hc;
+                g.out[o] = acc / (den + g.eps);
+                if (g.smax) g.smax[o] = m, g.sden[o] = den;
               }
+              m = -INFINITY, den = 0.f, acc = 0.f, d = d0;
             }
           }
-        }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[hb]);
-        if (kMode == 0) {
-          if (last_tile) {
-            if (d >= 0) {
-              const int64_t o = ((int64_t)d * H + h) * kEF + c;
-              g.out[o] = acc / (den + g.eps);
-              if (g.smax) g.smax[o] = m, g.sden[o] = den;
+          int po = mt[3 * kET] + hc;  // offset of the open segment's output element
+#pragma unroll 1
+          for (int cc = 0; cc < kET / 16; ++cc) {
+            float av[16], vv[16];
+            tmem_ld16(tbase + cc * 16, av);
+            tmem_ld16(tbase + 128 + cc * 16, vv);
+            tmem_ld_wait();
+            const uint32_t sflags = ((uint32_t)mt[4 * kET + (cc >> 1)]) >> ((cc & 1) * 16);
+            const uint32_t valid = ((uint32_t)mt[4 * kET + 4 + (cc >> 1)]) >> ((cc & 1) * 16);
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int t = cc * 16 + j;
+              const bool sf = (sflags >> j) & 1u;  // edge t opens a new segment: flush the finished one
+              const float q = acc * fast_rcp(den + g.eps);
+              if (sf) g.out[po] = q;
+              if (sf && g.smax != nullptr) g.smax[po] = m, g.sden[po] = den;
+              m = sf ? -INFINITY : m;
+              den = sf ? 0.f : den;
+              acc = sf ? 0.f : acc;
+              po = mt[3 * kET + t] + hc;
+              const float a = ((valid >> j) & 1u) ? av[j] + ba : -INFINITY;  // padding columns contribute exp(-inf) = 0
+              const float v = vv[j] + bm;
+              const float mn = fmaxf(m, a);
+              const float r = fast_exp(m - mn), p = fast_exp(a - mn);
+              den = fmaf(den, r, p);
+              acc = fmaf(acc, r, p * v);
+              m = mn;
             }
+          }
+          d = mt[nv - 1];
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[hb]);
+          if (last_tile) {
+            const int64_t o = (int64_t)d * hf + hc;
+            g.out[o] = acc / (den + g.eps);
+            if (g.smax) g.smax[o] = m, g.sden[o] = den;
           } else {
             cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc, cs[3 * kEF + c] = __int_as_float(d);
           }
+        } else {
+          float* pg = g.d_gate + (int64_t)e0 * hf + hc;
+          float* pm = g.d_msg + (int64_t)e0 * hf + hc;
+#pragma unroll 1
+          for (int cc = 0; cc < kET / 16; ++cc) {
+            float av[16], vv[16];
+            tmem_ld16(tbase + cc * 16, av);
+            tmem_ld16(tbase + 128 + cc * 16, vv);
+            tmem_ld_wait();
+            const uint32_t valid = ((uint32_t)mt[4 * kET + 4 + (cc >> 1)]) >> ((cc & 1) * 16);
+            // per-segment statistics re-read per column: same address for the ~max_nbr edges of a segment, so these
+            // are L1 hits; it keeps the column code free of branches and of load-latency bubbles
+            float sm[16], sd[16], so[16], sg_[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int o = mt[3 * kET + cc * 16 + j] + hc;
+              sm[j] = __ldg(g.smax + o), sd[j] = __ldg(g.sden + o), so[j] = __ldg(g.out + o), sg_[j] = __ldg(g.g_out + o);
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const float a = av[j] + ba, v = vv[j] + bm;
+              const float alpha = fast_exp(a - sm[j]) * fast_rcp(sd[j] + g.eps);
+              const float ag = alpha * sg_[j];
+              if ((valid >> j) & 1u) {
+                pm[(int64_t)(cc * 16 + j) * hf] = ag;
+                pg[(int64_t)(cc * 16 + j) * hf] = ag * (v - so[j]);
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[hb]);
         }
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < kEMmaWarp) {
     // ---------------------------------------------------------------- producers
     const int pt = tid - 128;
+    const uint32_t grp = (uint32_t)pt >> 8;  // stage cnt is produced by group (cnt & 1)
+    const int pl = pt & (kEGroup - 1);
     uint32_t cnt = 0;
     const uint8_t* w2[2] = {reinterpret_cast<const uint8_t*>(g.w2a), reinterpret_cast<const uint8_t*>(g.w2m)};
     const int64_t ldp = 4 * (int64_t)hhd, ldt = 2 * (int64_t)hhd;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int e0 = e_lo + tile * kET;
       const int nv = min(kET, e_hi - e0);
-      int32_t* mt = meta + (tile & (kEMetaBufs - 1)) * 3 * kET;
+      int32_t* mt = meta + (tile & (kEMetaBufs - 1)) * kEMetaStride;
       if (pt < kET) {
         const bool ok = pt < nv;
-        mt[pt] = ok ? g.dst[e0 + pt] : -1;
-        mt[kET + pt] = ok ? g.src[e0 + pt] : 0;
-        mt[2 * kET + pt] = ok ? g.rank[e0 + pt] : 0;
+        const int e = e0 + (ok ? pt : nv - 1);  // padding columns repeat the last valid edge (their B rows are zeros)
+        const int dd = g.dst[e];
+        mt[pt] = ok ? dd : -1;
+        mt[kET + pt] = g.src[e];
+        mt[2 * kET + pt] = g.rank[e];
+        mt[3 * kET + pt] = dd * H * kEF;
+        const bool sflag = ok && pt > 0 && g.dst[e - 1] != dd;  // a new segment starts here (never at t = 0)
+        const uint32_t sw = __ballot_sync(0xffffffffu, sflag), vw = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) mt[4 * kET + (pt >> 5)] = (int32_t)sw, mt[4 * kET + 4 + (pt >> 5)] = (int32_t)vw;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kEProducers) : "memory");
       // this thread's 4 (edge row, 16-byte chunk) slots of every stage
       int rd[4], rs[4], rr[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int r = (pt + kEProducers * j) >> 3;
-        rd[j] = mt[r], rs[j] = mt[kET + r], rr[j] = mt[2 * kET + r];
+        const int r = (pl + kEGroup * j) >> 3;
+        rd[j] = mt[r], rs[j] = mt[kET + r], rr[j] = mt[2 * kET + r];  // rd < 0 marks a padding row
       }
       for (int h = 0; h < H; ++h) {
         for (int net = 0; net < 2; ++net) {
           for (int kc = 0; kc < kcn; ++kc, ++cnt) {
+            if (kEProducers > kEGroup && (cnt & 1u) != grp) continue;
             const uint32_t s = cnt % kEStages, u = cnt / kEStages;
             mbar_wait(&empty[s], (u + 1) & 1u);
             uint8_t* st = stages + s * kEStageBytes;
-            if (pt == 0) {
+            if (pl == 0) {
               mbar_expect_tx(&full[s], kPackStageBytes);
               bulk_g2s(st, w2[net] + ((int64_t)h * kcn + kc) * kPackStageBytes, kPackStageBytes, &full[s]);
             }
@@ -244,7 +304,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             const int col0 = h * hd + kc * 32;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int cch = (pt + kEProducers * j) & 7;
+              const int cch = (pl + kEGroup * j) & 7;
               const int col = col0 + cch * 4;
               const bool ok = rd[j] >= 0 && (kc * 32 + cch * 4) < hd;
               pd[j] = ps[j] = te[j] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -257,7 +317,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             uint8_t* bh = st + kPackStageBytes;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int idx = pt + kEProducers * j;
+              const int idx = pl + kEGroup * j;
               float4 x;
               x.x = pd[j].x + ps[j].x + te[j].x;
               x.y = pd[j].y + ps[j].y + te[j].y;
@@ -323,7 +383,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     }
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kEMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -339,7 +399,7 @@ int check_edge_args(int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, 
   if (f != kEF) return fail(-2, "cgat_edge_attn_*: only F = 128 (vector attention) is instantiated");
   if (heads < 1 || heads > kEMaxHeads) return fail(-2, "cgat_edge_attn_*: heads must be in [1,8]");
   if (hd <= 0 || (hd & 3)) return fail(-2, "cgat_edge_attn_*: hidden width must be a multiple of 4");
-  if (n_atoms >= (1ll << 31) - 1 || n_edges >= (1ll << 31) - 129) return fail(-2, "cgat_edge_attn_*: size overflow");
+  if (n_atoms * heads * f >= (1ll << 31) || n_edges >= (1ll << 31) - 129) return fail(-2, "cgat_edge_attn_*: size overflow");
   return 0;
 }
 
