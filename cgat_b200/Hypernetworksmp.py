@@ -94,11 +94,19 @@ class HyperLinear(nn.Module):
         b = p[..., self.in_ch * self.out_ch:].reshape(*p.shape[:-1], 1, self.out_ch)
         return BatchLinear(weights=w, biases=b)
 
-    def apply_to(self, hyper_input, y):
-        """y_out[n] = W_n y[n] + b_n with (W_n, b_n) predicted from hyper_input[n]; fused."""
-        z = self.hypo_params.trunk(hyper_input)
+    def trunk_spec(self):
+        """([(W, b) of the tanh layers], (last weight, last bias, rows of the predicted matrix)) for ops.hyper_trunks."""
+        net = list(self.hypo_params.net)
+        last = net[-1]
+        return [(l.net[0].weight, l.net[0].bias) for l in net[:-1]], (last.weight, last.bias, self.in_ch * self.out_ch)
+
+    def apply_to(self, hyper_input, y, z=None, e=None):
+        """y_out[n] = W_n y[n] + b_n with (W_n, b_n) predicted from hyper_input[n]; fused.  z / e: this layer's
+        trunk output and bias tail when HyperFC has already run all trunks of the node layer in one kernel."""
+        if z is None:
+            z = self.hypo_params.trunk(hyper_input)
         last = self.hypo_params[-1]
-        return ops.hyper_linear(z, last.weight, last.bias, y, self.out_ch)
+        return ops.hyper_linear(z, last.weight, last.bias, y, self.out_ch, e=e)
 
 
 class HyperLayer(nn.Module):
@@ -112,8 +120,8 @@ class HyperLayer(nn.Module):
     def forward(self, hyper_input):
         return nn.Sequential(self.hyper_linear(hyper_input), self.norm_nl)
 
-    def apply_to(self, hyper_input, y):
-        y = self.hyper_linear.apply_to(hyper_input, y)
+    def apply_to(self, hyper_input, y, z=None, e=None):
+        y = self.hyper_linear.apply_to(hyper_input, y, z=z, e=e)
         return torch.tanh(F.layer_norm(y, (y.shape[-1],), eps=1e-5))
 
 
@@ -134,8 +142,11 @@ class HyperFC(nn.Module):
         return nn.Sequential(*[layer(hyper_input) for layer in self.layers])
 
     def apply_to(self, hyper_input, y):
-        for layer in self.layers:
-            y = layer.apply_to(hyper_input, y)
+        # all trunks see the same hyper-input: one chained kernel for the whole node layer (ops.hyper_trunks)
+        specs = [(l.hyper_linear if isinstance(l, HyperLayer) else l).trunk_spec() for l in self.layers]
+        zs, es = ops.hyper_trunks(hyper_input, [s[0] for s in specs], [s[1] for s in specs])
+        for layer, z, e in zip(self.layers, zs, es):
+            y = layer.apply_to(hyper_input, y, z=z, e=e)
         return y
 
 

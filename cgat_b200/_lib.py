@@ -32,7 +32,12 @@ SIGNATURES = {
     "cgat_gemm3x_tn": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _I32, _P]),
     "cgat_packed_floats": (_I64, [_I64, _I64]),
     "cgat_pack_kmajor": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
-    "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_trunk_packed_floats": (_I64, [_I32, _I32]),
+    "cgat_hyper_trunk_pack": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
+    "cgat_hyper_trunk_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "cgat_hyper_trunk_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
+    "cgat_gemm3x_tn_batched": (ctypes.c_int, [_P, _P, _I32, _I64, _I64, _P, _P, _I64, _I64, _I64, _I32, _P]),
     "cgat_hyper_rowscale_parts": (_I32, [_I64, _I32]),
     "cgat_hyper_rowscale": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_wgrad_splits": (_I32, [_I64]),
@@ -81,6 +86,15 @@ def ptr(t):
 
 def stream():
     return torch.cuda.current_stream().cuda_stream
+
+
+def ptr_array(tensors):
+    """HOST array of device pointers (for the entry points that take `const float* const*`)."""
+    return (ctypes.c_void_p * len(tensors))(*[ptr(t) for t in tensors])
+
+
+def i64_array(values):
+    return (ctypes.c_int64 * len(values))(*[int(v) for v in values])
 
 
 _prof = None  # list of (key, start_event, end_event, work) while profiling

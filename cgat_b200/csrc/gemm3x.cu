@@ -186,8 +186,9 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 // One 128 x 128 tile per CTA; split-K over blockIdx.z writes partial tiles that the caller sums.
 constexpr int kTnImage = 32 * 128;  // 32 K-rows x 128 B
 
+template <bool kSum>
 __device__ __forceinline__ void stage_chunk_mn(const float* __restrict__ src, int64_t ld, int col0, int n_cols,
-                                               int k0, int k_end, uint8_t* hi, uint8_t* lo, int tid) {
+                                               int k0, int k_end, uint8_t* hi, uint8_t* lo, int tid, float4& csum) {
   float4 v[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -195,6 +196,7 @@ __device__ __forceinline__ void stage_chunk_mn(const float* __restrict__ src, in
     const int gk = k0 + r, gc = col0 + q * 4;
     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gk < k_end && gc < n_cols) v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)gk * ld + gc));
+    if (kSum) csum.x += v[j].x, csum.y += v[j].y, csum.z += v[j].z, csum.w += v[j].w;  // q is fixed per thread
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -207,9 +209,23 @@ __device__ __forceinline__ void stage_chunk_mn(const float* __restrict__ src, in
   }
 }
 
+constexpr int kTnMaxBatch = 24;
+struct TnArgs {
+  const float* a[kTnMaxBatch];   // [K x M] row-major, one per batch entry
+  const float* b[kTnMaxBatch];   // [K x N]
+  float* c;                      // partial (split s, batch e) at c + s * split_stride + e * batch_stride
+  float* colsum;                 // optional: column sums of A, (n_split, batch, M)
+  int64_t lda, ldb, ldc, split_stride, batch_stride;
+  int M, N, K, k_per_split, n_split, batch;
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
-gemm3x_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-                 float* __restrict__ C, int64_t ldc, int64_t split_stride, int M, int N, int K, int k_per_split) {
+gemm3x_tn_kernel(const TnArgs g) {
+  const int entry = blockIdx.z / g.n_split, split = blockIdx.z - entry * g.n_split;
+  const float* __restrict__ A = g.a[entry];
+  const float* __restrict__ B = g.b[entry];
+  const int64_t lda = g.lda, ldb = g.ldb, ldc = g.ldc;
+  const int M = g.M, N = g.N, K = g.K, k_per_split = g.k_per_split;
   constexpr int kStages = 3, kOp = 4 * kTnImage;  // 16 KB per operand part
   constexpr int kStageBytes = 4 * kOp;
   extern __shared__ uint8_t smem_raw[];
@@ -221,7 +237,7 @@ gemm3x_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
-  const int k_begin = blockIdx.z * k_per_split;
+  const int k_begin = split * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
   const int nk = (k_end - k_begin + kKC - 1) / kKC;
   if (tid == 0) {
@@ -238,19 +254,35 @@ gemm3x_tn_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (warp < 4) {
+    const bool do_sum = g.colsum != nullptr && blockIdx.x == 0;
+    float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int kc = 0; kc < nk; ++kc) {
       const int s = kc % kStages, u = kc / kStages;
       mbar_wait(&empty[s], (u + 1) & 1);
       uint8_t* st = smem + s * kStageBytes;
-      stage_chunk_mn(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + kOp, tid);
-      stage_chunk_mn(B, ldb, n0, N, k_begin + kc * kKC, k_end, st + 2 * kOp, st + 3 * kOp, tid);
+      if (do_sum) stage_chunk_mn<true>(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + kOp, tid, csum);
+      else stage_chunk_mn<false>(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + kOp, tid, csum);
+      stage_chunk_mn<false>(B, ldb, n0, N, k_begin + kc * kKC, k_end, st + 2 * kOp, st + 3 * kOp, tid, csum);
       fence_async_smem();
       mbar_arrive(&full[s]);
     }
     mbar_wait(accum, 0);
     tc_fence_after();
+    if (do_sum) {
+      // column sums of A over this split's rows (bias gradients): lane = column group, the 4 warps hold
+      // disjoint row sets; the operand stages are free again once `accum` has fired
+      float4* red = reinterpret_cast<float4*>(smem);
+      red[tid] = csum;
+      asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
+      const float* rf = reinterpret_cast<const float*>(smem);
+      const int q = tid >> 2, comp = tid & 3;
+      float t = 0.f;
+#pragma unroll
+      for (int w = 0; w < 4; ++w) t += rf[(w * 32 + q) * 4 + comp];
+      if (m0 + tid < M) g.colsum[((int64_t)split * g.batch + entry) * M + m0 + tid] = t;
+    }
     const int m = m0 + warp * 32 + lane;
-    float* cbase = C + (int64_t)blockIdx.z * split_stride;
+    float* cbase = g.c + (int64_t)split * g.split_stride + (int64_t)entry * g.batch_stride;
 #pragma unroll 1
     for (int cc = 0; cc < 4; ++cc) {
       float v[32], w[32];
@@ -328,26 +360,61 @@ extern "C" int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64
   return launch_gemm<128>(A, lda, B, ldb, bias, C, ldc, (int)M, (int)N, (int)K, act, stream);
 }
 
-// C[split][M,N] = sum over this split's rows k of A[k,m] * B[k,n].  n_split partial results, `split_stride`
-// floats apart (the caller sums them: keeps the K/8-step accumulation short and fills the SMs).
-extern "C" int cgat_gemm3x_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
-                              int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (M <= 0 || N <= 0 || n_split <= 0) return 0;
-  if ((M & 3) || (N & 3) || (lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
-      (reinterpret_cast<uintptr_t>(B) & 15))
-    return fail(-2, "cgat_gemm3x_tn: M, N, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
-  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return fail(-2, "cgat_gemm3x_tn: size overflow");
+namespace {
+int launch_tn(const TnArgs& a, cudaStream_t stream) {
   constexpr int kSmem = 3 * 4 * 4 * kTnImage + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     CGAT_CUDA(cudaFuncSetAttribute(gemm3x_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
     configured = true;
   }
+  dim3 grid((unsigned)ceil_div(a.N, 128), (unsigned)ceil_div(a.M, 128), (unsigned)(a.n_split * a.batch));
+  gemm3x_tn_kernel<<<grid, kThreads, kSmem, stream>>>(a);
+  return check_launch("gemm3x_tn_kernel");
+}
+
+int check_tn(const float* A, const float* B, int64_t lda, int64_t ldb, int64_t M, int64_t N, int64_t K) {
+  if ((M & 3) || (N & 3) || (lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15))
+    return fail(-2, "cgat_gemm3x_tn: M, N, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return fail(-2, "cgat_gemm3x_tn: size overflow");
+  return 0;
+}
+}  // namespace
+
+// C[split][M,N] = sum over this split's rows k of A[k,m] * B[k,n].  n_split partial results, `split_stride`
+// floats apart (the caller sums them: keeps the K/8-step accumulation short and fills the SMs).
+extern "C" int cgat_gemm3x_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                              int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split, void* stream_) {
+  if (M <= 0 || N <= 0 || n_split <= 0) return 0;
+  if (int e = check_tn(A, B, lda, ldb, M, N, K)) return e;
   int k_per_split = (int)ceil_div(ceil_div(K, n_split), kKC) * kKC;
   if (k_per_split == 0) k_per_split = kKC;
-  dim3 grid((unsigned)ceil_div(N, 128), (unsigned)ceil_div(M, 128), (unsigned)n_split);
-  gemm3x_tn_kernel<<<grid, kThreads, kSmem, stream>>>(A, lda, B, ldb, C, ldc, split_stride, (int)M, (int)N, (int)K,
-                                                      k_per_split);
-  return check_launch("gemm3x_tn_kernel");
+  TnArgs a{};
+  a.a[0] = A, a.b[0] = B, a.c = C, a.colsum = nullptr;
+  a.lda = lda, a.ldb = ldb, a.ldc = ldc, a.split_stride = split_stride, a.batch_stride = 0;
+  a.M = (int)M, a.N = (int)N, a.K = (int)K, a.k_per_split = k_per_split, a.n_split = n_split, a.batch = 1;
+  return launch_tn(a, (cudaStream_t)stream_);
+}
+
+// Batched form: C[s][e] = sum over split s of A_e^T B_e for `batch` (<= 24) operand pairs of identical shape
+// (the 20 weight gradients of a node layer's hypernetwork trunks in one launch).  A, B: HOST arrays of device
+// pointers.  C: (n_split, batch, M, N) contiguous.  colsum (optional): (n_split, batch, M) column sums of A_e
+// over the split's rows — the bias gradients, produced while the operand is staged.
+extern "C" int cgat_gemm3x_tn_batched(const float* const* A, const float* const* B, int32_t batch, int64_t lda,
+                                      int64_t ldb, float* C, float* colsum, int64_t M, int64_t N, int64_t K,
+                                      int32_t n_split, void* stream_) {
+  if (M <= 0 || N <= 0 || n_split <= 0 || batch <= 0) return 0;
+  if (batch > kTnMaxBatch) return fail(-2, "cgat_gemm3x_tn_batched: at most 24 operand pairs per call");
+  TnArgs a{};
+  for (int e = 0; e < batch; ++e) {
+    if (int err = check_tn(A[e], B[e], lda, ldb, M, N, K)) return err;
+    a.a[e] = A[e], a.b[e] = B[e];
+  }
+  int k_per_split = (int)ceil_div(ceil_div(K, n_split), kKC) * kKC;
+  if (k_per_split == 0) k_per_split = kKC;
+  a.c = C, a.colsum = colsum;
+  a.lda = lda, a.ldb = ldb, a.ldc = N, a.split_stride = (int64_t)batch * M * N, a.batch_stride = M * N;
+  a.M = (int)M, a.N = (int)N, a.K = (int)K, a.k_per_split = k_per_split, a.n_split = n_split, a.batch = batch;
+  return launch_tn(a, (cudaStream_t)stream_);
 }

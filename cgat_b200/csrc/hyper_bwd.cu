@@ -166,8 +166,9 @@ hyper_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ y, con
 using namespace cgat;
 
 extern "C" int32_t cgat_hyper_wgrad_splits(int64_t n_atoms) {
-  int64_t s = (n_atoms + 2047) / 2048;
-  return (int32_t)(s < 1 ? 1 : (s > 4 ? 4 : s));
+  // grid = 64 channel pairs x splits on 148 SMs: 2 splits = 128 CTAs (one wave, 86 % of the SMs); 3 would be
+  // 192 CTAs = two waves with the second one a third full
+  return n_atoms > 1024 ? 2 : 1;
 }
 
 // out: (cgat_hyper_wgrad_splits(N), F*F, F) partial dL/dW[:F*F]; sum over dim 0.

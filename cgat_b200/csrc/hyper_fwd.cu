@@ -27,7 +27,7 @@ template <int F>
 struct HyperCfg {
   static constexpr int kKC = F / kPackChunk;                    // K chunks of 32 floats
   static constexpr int kABytes = kKC * (int)kPackStageBytes;    // z tile, hi+lo per chunk
-  static constexpr int kStages = 3;
+  static constexpr int kStages = 3;                             // 128 KB z tile (hi+lo) + 3 x 32 KB weight stages = 224 KB
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + 1024 + kBarBytes;
   static constexpr int kThreads = 288;
@@ -45,7 +45,8 @@ struct HyperCfg {
 template <int F, int kMode>
 __global__ void __launch_bounds__(HyperCfg<F>::kThreads, 1)
 hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
-                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
+                        const float* __restrict__ e_term2, const float* __restrict__ w_packed,
+                        float* __restrict__ y_out, int n_atoms, int oc) {
   using Cfg = HyperCfg<F>;
   static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
   extern __shared__ uint8_t smem_raw[];
@@ -65,6 +66,10 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
   const int n_tiles = (n_atoms + 127) / 128;
   const int n_chunks = F / oc;
   const int n_items = n_tiles * n_chunks;
+  // work item = (atom tile, chunk of output channels), chunk fastest; every CTA owns a CONTIGUOUS range, so the
+  // z tile (A operand, 64 KB) is restaged only when the atom tile changes (~once or twice per CTA)
+  const int item_lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
@@ -88,8 +93,8 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
   if (warp < 4) {
     // ------------------------------------------------------------------ epilogue
     uint32_t ocount = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-      const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int tile = item / n_chunks, chunk = item - tile * n_chunks;
       const int n = tile * 128 + warp * 32 + lane;
       const bool valid = n < n_atoms;
       float y[F];  // kMode 0: this atom's y_in row; kMode 1: the running partial sums over o
@@ -120,7 +125,11 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[b]);
-        if (kMode == 0 && valid) y_out[(int64_t)n * F + o] = acc + __ldg(e_term + (int64_t)n * F + o);
+        if (kMode == 0 && valid) {
+          float e = __ldg(e_term + (int64_t)n * F + o);
+          if (e_term2 != nullptr) e += __ldg(e_term2 + (int64_t)n * F + o);
+          y_out[(int64_t)n * F + o] = acc + e;
+        }
       }
       if (kMode == 1 && valid) {
         float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F);
@@ -132,11 +141,14 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
     // ------------------------------------------------------------------ z-tile stagers + weight TMA
     const int st = tid - 128;  // 0..127
     uint32_t it = 0, cnt = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      const int chunk = item / n_tiles, tile = item - chunk * n_tiles;
-      mbar_wait(a_free, (it + 1) & 1u);  // previous item's MMAs have finished reading the z tile
+    int staged_tile = -1;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int tile = item / n_chunks, chunk = item - tile * n_chunks;
+      const bool restage = tile != staged_tile;
+      staged_tile = tile;
+      if (restage) mbar_wait(a_free, (it + 1) & 1u);  // the previous tile's MMAs have finished reading the z tile
 #pragma unroll 1
-      for (int kc = 0; kc < Cfg::kKC; ++kc) {
+      for (int kc = 0; restage && kc < Cfg::kKC; ++kc) {
         float4 v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -156,8 +168,11 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
           *reinterpret_cast<float4*>(hi + kPackImageBytes + off) = l;
         }
       }
-      fence_async_smem();
-      mbar_arrive(a_full);
+      if (restage) {
+        fence_async_smem();
+        mbar_arrive(a_full);
+        ++it;
+      }
       if (st == 0) {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_packed);
         for (int oi = 0; oi < oc; ++oi) {
@@ -177,8 +192,14 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
     // ------------------------------------------------------------------ MMA issuer
     constexpr uint32_t idesc = umma_idesc_tf32(128, F);
     uint32_t it = 0, cnt = 0, ocount = 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-      mbar_wait(a_full, it & 1u);
+    int staged_tile = -1;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int tile = item / n_chunks;
+      if (tile != staged_tile) {
+        mbar_wait(a_full, it & 1u);
+        ++it;
+        staged_tile = tile;
+      }
       tc_fence_after();
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
         const uint32_t b = ocount & 1u;
@@ -205,7 +226,8 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
           __syncwarp();
         }
       }
-      if (lane == 0) umma_commit(a_free);
+      // last item of this atom tile: the z tile may be overwritten once these MMAs are done
+      if ((item + 1 == item_hi || (item + 1) / n_chunks != tile) && lane == 0) umma_commit(a_free);
       __syncwarp();
     }
   }
@@ -231,8 +253,8 @@ int hyper_chunk(int64_t n_atoms, int f) {
 }
 
 template <int kMode>
-int launch_hyper(const float* z, const float* y_in, const float* e_term, const float* w_packed, float* y_out,
-                 int64_t n_atoms, int32_t f, cudaStream_t stream) {
+int launch_hyper(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_packed,
+                 float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {
   if (n_atoms <= 0) return 0;
   if (f != 128) return fail(-2, "cgat_hyper_*: only F = 128 is instantiated");
   if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_*: too many atoms");
@@ -247,17 +269,18 @@ int launch_hyper(const float* z, const float* y_in, const float* e_term, const f
   const int oc = hyper_chunk(n_atoms, f);
   const int n_items = n_tiles * (f / oc);
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
-  hyper_rowdot_fwd_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(z, y_in, e_term, w_packed, y_out,
-                                                                                         (int)n_atoms, oc);
+  hyper_rowdot_fwd_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
+      z, y_in, e_term, e_term2, w_packed, y_out, (int)n_atoms, oc);
   return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");
 }
 }  // namespace
 
 // y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) y_in[n,i] + e_term[n,o]
-//   z, y_in, e_term, y_out: (n_atoms, F) fp32 contiguous; w_packed: cgat_pack_kmajor of W[:F*F, :F]
-extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
-                                     float* y_out, int64_t n_atoms, int32_t f, void* stream_) {
-  return launch_hyper<0>(z, y_in, e_term, w_packed, y_out, n_atoms, f, (cudaStream_t)stream_);
+//   z, y_in, e_term, e_term2 (optional, added to e_term), y_out: (n_atoms, F) fp32 contiguous;
+//   w_packed: cgat_pack_kmajor of W[:F*F, :F]
+extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* e_term2,
+                                     const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, void* stream_) {
+  return launch_hyper<0>(z, y_in, e_term, e_term2, w_packed, y_out, n_atoms, f, (cudaStream_t)stream_);
 }
 
 // number of partial results cgat_hyper_rowscale writes for this problem size
@@ -268,5 +291,5 @@ extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { retur
 //   partial: (cgat_hyper_rowscale_parts, n_atoms, F)
 extern "C" int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_packed, float* partial,
                                    int64_t n_atoms, int32_t f, void* stream_) {
-  return launch_hyper<1>(a, scale, nullptr, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
+  return launch_hyper<1>(a, scale, nullptr, nullptr, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
 }

@@ -79,6 +79,7 @@ LEAKY_SLOPE = 0.01
 # numerics A/B switch for development (1 = fused tensor-core kernels; 0 = library GEMMs + segment kernels)
 _FUSED = os.environ.get("CGAT_B200_FUSED", "1") != "0"
 _TN_WGRAD = os.environ.get("CGAT_B200_TN", "1") != "0"   # weight gradients on cgat_gemm3x_tn vs library mm
+_TRUNK = os.environ.get("CGAT_B200_TRUNK", "1") != "0"   # hypernetwork trunks: fused chain kernel vs library GEMMs
 
 
 def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
@@ -147,7 +148,7 @@ def gemm3x_tn(a, b, n_split=None):
         raise ValueError("gemm3x_tn needs row-contiguous CUDA operands")
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if n_split is None:
-        n_split = max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+        n_split = max(1, min((K + 255) // 256, (2 * 148 + tiles - 1) // tiles))
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_tn", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), part.data_ptr(), N, M * N,
               M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_tn", bound="tensor", flops=2.0 * M * N * K))
@@ -179,22 +180,27 @@ def packed_kmajor(w, rows=None, transpose=False):
 class _HyperLinear(torch.autograd.Function):
     """y_out[n] = reshape(W z[n] + b)[:F*F] y[n] + (W z[n] + b)[F*F:]   (reference HyperLinear.forward +
     BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209) with the (N, F*F+F) predicted-weight
-    tensor never materialised in forward (cgat_hyper_rowdot_fwd)."""
+    tensor never materialised in forward (cgat_hyper_rowdot_fwd).  `e` (optional) is the z-part of the
+    bias tail, W[F*F:] z + b[F*F:], when the fused trunk kernel has already produced it."""
 
     @staticmethod
-    def forward(ctx, z, weight, bias, y, w_packed, w_packed_bt):
+    def forward(ctx, z, weight, bias, y, e, w_packed, w_packed_bt):
         z, y = _f32c(z), _f32c(y)
         n, f = y.shape
         ff = f * f
-        # bias-shaped remainder: e = [y | z] @ [bl.view(F,F) | W[F*F:]]^T + bl[F*F:]
-        we = torch.cat([bias[:ff].view(f, f), weight[ff:]], dim=1)
-        e = gemm3x(torch.cat([y, z], dim=1), we, bias[ff:].contiguous())
+        if e is None:
+            # bias-shaped remainder: e = [y | z] @ [bl.view(F,F) | W[F*F:]]^T + bl[F*F:]
+            we = torch.cat([bias[:ff].view(f, f), weight[ff:]], dim=1)
+            e1, e2 = gemm3x(torch.cat([y, z], dim=1), we, bias[ff:].contiguous()), None
+        else:
+            e1, e2 = _f32c(e), gemm3x(y, bias[:ff].view(f, f))
         out = torch.empty_like(y)
-        _lib.call("cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y), _lib.ptr(e), _lib.ptr(w_packed),
+        _lib.call("cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y), _lib.ptr(e1), _lib.ptr(e2), _lib.ptr(w_packed),
                   _lib.ptr(out), n, f, _lib.stream(),
                   work=dict(key="hyper_rowdot_fwd", bound="tensor", flops=2.0 * n * f * ff,
                             note="3xTF32: 3 tensor passes per algorithmic flop"))
         ctx.save_for_backward(z, weight, bias, y, w_packed, w_packed_bt)
+        ctx.has_e = e is not None
         return out
 
     @staticmethod
@@ -211,11 +217,13 @@ class _HyperLinear(torch.autograd.Function):
         _lib.call("cgat_hyper_rowscale", _lib.ptr(z), _lib.ptr(g), _lib.ptr(w_packed), _lib.ptr(buf), n, f,
                   _lib.stream(), work=work)
         g_y = buf.sum(dim=0) + gemm3x(g, bias[:ff].view(f, f).t().contiguous())
-        # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ bias rows)
+        # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ the bias-tail rows unless they went through `e`)
         buf2 = torch.empty_like(buf)
         _lib.call("cgat_hyper_rowscale", _lib.ptr(y), _lib.ptr(g), _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
                   _lib.stream(), work=work)
-        g_z = buf2.sum(dim=0) + gemm3x(g, weight[ff:].t().contiguous())
+        g_z = buf2.sum(dim=0)
+        if not ctx.has_e:
+            g_z = g_z + gemm3x(g, weight[ff:].t().contiguous())
         # weight gradient: dW[o*F+i,k] = sum_n g[n,o] y[n,i] z[n,k] — contraction over atoms, outer product on the fly
         lib = _lib.load()
         splits = int(lib.cgat_hyper_wgrad_splits(n))
@@ -229,23 +237,150 @@ class _HyperLinear(torch.autograd.Function):
         else:
             torch.sum(wpart, dim=0, out=g_w[:ff])
         yz = torch.cat([y, z], dim=1)                      # bias-shaped rows: g^T [y | z]
-        gyz = gemm3x_tn(g, yz, 1)                          # (F, 2F)
+        gyz = gemm3x_tn(g, yz)                             # (F, 2F), split over atoms to fill the SMs
         g_w[ff:] = gyz[:, f:]
         g_b = torch.cat([gyz[:, :f].reshape(ff), g.sum(dim=0)])
-        return g_z, g_w, g_b, g_y, None, None
+        return g_z, g_w, g_b, g_y, (g if ctx.has_e else None), None, None
 
 
-def hyper_linear(z, weight, bias, y, out_ch):
+def hyper_linear(z, weight, bias, y, out_ch, e=None):
     """y_out[n] = reshape(weight z[n] + bias)[:out*in] y[n] + (...)[out*in:]
-    (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209)."""
+    (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209).
+    `e`: weight[out*in:] z + bias[out*in:] if hyper_trunks has already computed it (fused path only)."""
     in_ch = y.shape[1]
     if _FUSED and z.is_cuda and in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
-        return _HyperLinear.apply(z, weight, bias, y, packed_kmajor(weight, in_ch * out_ch),
+        return _HyperLinear.apply(z, weight, bias, y, e, packed_kmajor(weight, in_ch * out_ch),
                                   packed_kmajor(weight, in_ch * out_ch, 2) if torch.is_grad_enabled() else None)
     p = torch.addmm(bias, z, weight.t())                            # (N, out*in + out)
     w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
     b = p[:, in_ch * out_ch:]
     return torch.baddbmm(b.unsqueeze(2), w, y.unsqueeze(2)).squeeze(2)
+
+
+# ----------------------------------------------------------------------------------------------
+# Hypernetwork trunks: the J FCBlocks of a node layer share their input (reference
+# CGAT/Hypernetworksmp.py:36-83, 243-254); one chained tensor-core kernel runs all of them.
+# ----------------------------------------------------------------------------------------------
+_TRUNK_STEPS = 5
+
+
+def gemm3x_tn_batched(a_list, b_list, colsum=True):
+    """[a.T @ b for a, b in zip(a_list, b_list)] in one launch (cgat_gemm3x_tn_batched): all operands
+    (K, 128*m) row-contiguous with identical shapes.  Returns (C (batch, M, N), column sums of a (batch, M))."""
+    K, M = a_list[0].shape
+    N = b_list[0].shape[1]
+    batch = len(a_list)
+    dev = a_list[0].device
+    tiles = batch * ((M + 127) // 128) * ((N + 127) // 128)
+    n_split = max(1, min((K + 255) // 256, (2 * 148) // tiles))
+    part = torch.empty((n_split, batch, M, N), dtype=torch.float32, device=dev)
+    csum = torch.empty((n_split, batch, M), dtype=torch.float32, device=dev) if colsum else None
+    _lib.call("cgat_gemm3x_tn_batched", _lib.ptr_array(a_list), _lib.ptr_array(b_list), batch, a_list[0].stride(0),
+              b_list[0].stride(0), _lib.ptr(part), _lib.ptr(csum), M, N, K, n_split, _lib.stream(),
+              work=dict(key="gemm3x_tn_batched", bound="tensor", flops=2.0 * batch * M * N * K))
+    if n_split == 1:
+        return part[0], (csum[0] if colsum else None)
+    return part.sum(dim=0), (csum.sum(dim=0) if colsum else None)
+
+
+def _trunk_packed(weights, transpose):
+    """Packed chain operands of a list of F x F weights (cgat_hyper_trunk_pack), cached on the first tensor and
+    keyed by the autograd versions / addresses of all of them (an optimizer step triggers a repack)."""
+    key = tuple((w._version, w.data_ptr()) for w in weights)
+    cache = weights[0].__dict__.setdefault("_cgat_trunk_packed", {})
+    hit = cache.get(transpose)
+    if hit is not None and hit[0] == key:
+        return hit[1]
+    lib = _lib.load()
+    f = weights[0].shape[1]
+    buf = hit[1] if hit is not None else torch.empty(int(lib.cgat_hyper_trunk_packed_floats(len(weights), f)),
+                                                     dtype=torch.float32, device=weights[0].device)
+    if any(w.stride(1) != 1 for w in weights):
+        raise ValueError("trunk weights must be row-contiguous")
+    _lib.call("cgat_hyper_trunk_pack", _lib.ptr_array([w.detach() for w in weights]),
+              _lib.i64_array([w.stride(0) for w in weights]), len(weights), f, transpose, _lib.ptr(buf), _lib.stream(),
+              work=dict(key="hyper_trunk_pack", bound="hbm", bytes=12.0 * len(weights) * f * f))
+    cache[transpose] = (key, buf)
+    return buf
+
+
+class _HyperTrunk(torch.autograd.Function):
+    """(Z, E) = trunks(h): Z[j] = t4 of hyper-layer j, E[j] = We_j Z[j] + be_j; see cgat_hyper_trunk_fwd.
+    flat = per j: W1, b1, W2, b2, W3, b3, W4, b4, We, be (We / be detached: their gradients are produced by
+    _HyperLinear, which owns the whole last Linear)."""
+
+    @staticmethod
+    def forward(ctx, h, n_j, *flat):
+        h = _f32c(h)
+        n, f = h.shape
+        per = 2 * _TRUNK_STEPS
+        ws = [flat[j * per + 2 * s] for j in range(n_j) for s in range(_TRUNK_STEPS)]
+        bs = [flat[j * per + 2 * s + 1].contiguous() for j in range(n_j) for s in range(_TRUNK_STEPS)]
+        T = torch.empty((n_j, 4, n, f), dtype=torch.float32, device=h.device)
+        E = torch.empty((n_j, n, f), dtype=torch.float32, device=h.device)
+        _lib.call("cgat_hyper_trunk_fwd", _lib.ptr(h), _lib.ptr(_trunk_packed(ws, 0)), _lib.ptr_array(bs), _lib.ptr(T),
+                  _lib.ptr(E), n, f, n_j, _lib.stream(),
+                  work=dict(key="hyper_trunk_fwd", bound="tensor", flops=2.0 * n * f * f * _TRUNK_STEPS * n_j,
+                            note="3xTF32 chain of 5 GEMMs per hyper-layer, activation tile resident on the SM"))
+        ctx.save_for_backward(h, T, *ws)
+        ctx.n_j = n_j
+        return T[:, 3], E
+
+    @staticmethod
+    def backward(ctx, dZ, dE):
+        h, T = ctx.saved_tensors[:2]
+        ws = ctx.saved_tensors[2:]
+        n_j = ctx.n_j
+        n, f = h.shape
+        dev = h.device
+        dZ = torch.zeros((n_j, n, f), dtype=torch.float32, device=dev) if dZ is None else _f32c(dZ)
+        dE = torch.zeros((n_j, n, f), dtype=torch.float32, device=dev) if dE is None else _f32c(dE)
+        # backward chain order per j: We, W4, W3, W2, W1 (transposed operands)
+        wt = [ws[j * _TRUNK_STEPS + s] for j in range(n_j) for s in (4, 3, 2, 1, 0)]
+        D = torch.empty((n_j, 4, n, f), dtype=torch.float32, device=dev)
+        dH = torch.empty((n_j, n, f), dtype=torch.float32, device=dev)
+        _lib.call("cgat_hyper_trunk_bwd", _lib.ptr(dE), _lib.ptr(dZ), _lib.ptr(T), _lib.ptr(_trunk_packed(wt, 1)),
+                  _lib.ptr(D), _lib.ptr(dH), n, f, n_j, _lib.stream(),
+                  work=dict(key="hyper_trunk_bwd", bound="tensor", flops=2.0 * n * f * f * _TRUNK_STEPS * n_j,
+                            note="3xTF32 chain of 5 GEMMs per hyper-layer, activation tile resident on the SM"))
+        g_h = dH[0] if n_j == 1 else dH.sum(dim=0)
+        # weight / bias gradients of the 4 tanh layers of every trunk in one launch: dW_s = D_s^T (input of layer s)
+        a_list = [D[j, s] for j in range(n_j) for s in range(4)]
+        b_list = [h if s == 0 else T[j, s - 1] for j in range(n_j) for s in range(4)]
+        g_w, g_b = gemm3x_tn_batched(a_list, b_list)
+        grads = []
+        for j in range(n_j):
+            for s in range(4):
+                grads += [g_w[j * 4 + s], g_b[j * 4 + s]]
+            grads += [None, None]
+        return (g_h, None, *grads)
+
+
+def hyper_trunks(h, layers, tails):
+    """The trunks of the J hyper-layers of a node layer on their shared hyper-input h.
+    layers[j] = [(W, b), ...] tanh layers (reference FCBlock, CGAT/Hypernetworksmp.py:36-83);
+    tails[j] = (weight, bias, rows) of the last Linear, whose rows [rows:] are the bias tail.
+    Returns (zs, es): z_j and, on the fused path, e_j = weight[rows:] z_j + bias[rows:] (else None)."""
+    n_j = len(layers)
+    f = h.shape[1]
+    fused = (_FUSED and _TRUNK and h.is_cuda and f == 128 and 1 <= n_j <= 4
+             and all(len(l) == 4 and all(w.shape == (f, f) for w, _ in l) for l in layers)
+             and all(w.shape[0] - rows == f and w.shape[1] == f for w, _, rows in tails))
+    if not fused:
+        zs = []
+        for l in layers:
+            z = h
+            for w, b in l:
+                z = torch.tanh(torch.nn.functional.linear(z, w, b))
+            zs.append(z)
+        return zs, [None] * n_j
+    flat = []
+    for l, (w, b, rows) in zip(layers, tails):
+        for wi, bi in l:
+            flat += [wi, bi]
+        flat += [w.detach()[rows:], b.detach()[rows:]]
+    Z, E = _HyperTrunk.apply(h, n_j, *flat)
+    return list(Z.unbind(0)), list(E.unbind(0))
 
 
 def _w2_transposed_packed(w2, heads):

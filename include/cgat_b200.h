@@ -82,6 +82,13 @@ int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64_t ldb, con
  * MN-major (no transposed copies).  n_split partial results `split_stride` floats apart.          */
 int cgat_gemm3x_tn(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
                    int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split, void* stream);
+/* Batched form for `batch` (<= 24) operand pairs of identical shape — all weight gradients of a node layer's
+ * hypernetwork trunks in one launch.  A, B: HOST arrays of device pointers.  C: (n_split, batch, M, N).
+ * colsum (optional, may be NULL): (n_split, batch, M) column sums of A_e over the split's rows (the bias
+ * gradients of the same nn.Linear backward), produced while the operand is staged.                      */
+int cgat_gemm3x_tn_batched(const float* const* A, const float* const* B, int32_t batch, int64_t lda, int64_t ldb,
+                           float* C, float* colsum, int64_t M, int64_t N, int64_t K, int32_t n_split,
+                           void* stream);
 
 /* ---- packed tensor-core operands ---------------------------------------------------------------
  * fp32 [rows x k] (transpose=1: given as [k x rows]; transpose=2: each 128x128 block transposed)
@@ -96,9 +103,29 @@ int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_
  * y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) * y_in[n,i] + e_term[n,o]
  * Replaces Linear(F -> F*F+F) + view + BatchLinear (reference CGAT/Hypernetworksmp.py:243-254,
  * 205-209) without materialising the (N, F*F+F) predicted-weight tensor.  w_packed =
- * cgat_pack_kmajor(W[:F*F,:F]); e_term carries the bias-shaped remainder (see hyper_fwd.cu).   */
-int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* w_packed,
-                          float* y_out, int64_t n_atoms, int32_t f, void* stream);
+ * cgat_pack_kmajor(W[:F*F,:F]); e_term (+ optional e_term2, may be NULL) carry the bias-shaped
+ * remainder (see hyper_fwd.cu).                                                                   */
+int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* e_term2,
+                          const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, void* stream);
+
+/* ---- fused hypernetwork trunks -------------------------------------------
+ * The J (<= 4) HyperLinears of a node layer share the hyper-input h; each runs
+ *   t1 = tanh(W1 h + b1) ... t4 = z = tanh(W4 t3 + b4)     (FCBlock, reference CGAT/Hypernetworksmp.py:36-83)
+ *   e  = We z + be   with We = last.weight[F*F:], be = last.bias[F*F:]   (bias tail of :243-254)
+ * One persistent kernel runs the 5-GEMM chain per (128-atom tile, j) with the activation tile resident in
+ * shared memory / TMEM between layers (replaces 20 cuBLAS + 16 tanh launches per node layer, forward).
+ *   cgat_hyper_trunk_pack: HOST array of n_mats (<= 24) device pointers to F x F matrices -> packed chain
+ *     operands; forward order per j: W1,W2,W3,W4,We (transpose=0); backward: We,W4,W3,W2,W1 (transpose=1).
+ *   fwd: T (J,4,N,F) tanh outputs (saved for backward; T[j][3] = z_j), E (J,N,F).
+ *   bwd: D[j][3] = (dE[j] We + dZ[j]) * (1 - T[j][3]^2), D[j][s-1] = (D[j][s] W_{s+1}) * (1 - T[j][s-1]^2),
+ *        dH[j] = D[j][0] W1;  D (J,4,N,F) feeds cgat_gemm3x_tn_batched for the weight / bias gradients.   */
+int64_t cgat_hyper_trunk_packed_floats(int32_t n_mats, int32_t f);
+int cgat_hyper_trunk_pack(const float* const* weights, const int64_t* ld, int32_t n_mats, int32_t f,
+                          int32_t transpose, float* out, void* stream);
+int cgat_hyper_trunk_fwd(const float* h, const float* w_packed, const float* const* biases, float* T, float* E,
+                         int64_t n_atoms, int32_t f, int32_t J, void* stream);
+int cgat_hyper_trunk_bwd(const float* dE, const float* dZ, const float* T, const float* wt_packed, float* D,
+                         float* dH, int64_t n_atoms, int32_t f, int32_t J, void* stream);
 
 /* ---- fused edge attention, forward ---------------------------------
  * out[d,h,:] = sum_{t in in(d)} softmax_t(a_t,h)[:] * v_t,h[:] with

@@ -41,7 +41,7 @@ def install(monkeypatch):
             monkeypatch.setattr(mod, "build_segment_plan", build_segment_plan)
     monkeypatch.setattr(ops, "seg_softmax", seg_softmax)
 
-    def hyper_linear(z, weight, bias, y, out_ch):
+    def hyper_linear(z, weight, bias, y, out_ch, e=None):
         in_ch = y.shape[1]
         p = torch.addmm(bias, z, weight.t())
         w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
