@@ -45,6 +45,7 @@ struct DgradArgs {
   const float* wt_m;
   float* G;                // (N, ldg); this pass writes columns [col_off, col_off + 2*H*Hd)
   float* d_rank;           // (grid, n_ranks, 2*H*Hd) partial dL/dT per CTA, or null
+  float* d_pre;            // (E, 2*H*Hd) per-edge pre-activation gradients in THIS edge order, or null
   int64_t ldg;
   int col_off, n_atoms, n_edges, heads, hd, n_ranks;
 };
@@ -117,6 +118,57 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
     const int c = warp * 32 + lane;
     const uint32_t bitpos = (uint32_t)((lane & 3) * 8 + (lane >> 2));
     uint32_t icount = 0;
+    if (g.d_pre != nullptr) {
+      // Lean epilogue: d_pre[e, col] = d_hid * leaky_relu'(pre), one 128-byte line per warp and edge; every
+      // segment / rank sum is taken from this copy by the HBM-bound cgat_edge_attn_reduce, so the per-column
+      // work here is an add, a select, a multiply and a store.
+      const int64_t ldd = 2 * (int64_t)hhd;
+      for (int item = 0; item < n_items; ++item) {
+        const int net = item / (H * nhalf), h = (item / nhalf) % H, half = item % nhalf;
+        const int kk = half * 128 + c;
+        const bool kvalid = kk < hd;
+        const int col = net * hhd + h * hd + kk;
+        const uint32_t* sg = g.signs + ((int64_t)(net * H + h) * kcn + (half * 4 + warp)) * g.n_edges;
+        for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
+          const int e0 = e_lo + tile * kBT;
+          const int nv = min(kBT, e_hi - e0);
+          const uint32_t b = icount & 1u;
+          mbar_wait(&tmem_full[b], (icount >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + b * 256;
+          float* prow = g.d_pre + (int64_t)e0 * ldd + col;
+#pragma unroll 1
+          for (int cc = 0; cc < kBT / 32; ++cc) {
+            uint32_t wd[32];
+            const uint4* sp = reinterpret_cast<const uint4*>(sg + e0 + cc * 32);
+            const bool aligned = ((reinterpret_cast<uintptr_t>(sp) & 15) == 0) && (cc * 32 + 32 <= nv);
+            if (aligned) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const uint4 q = kvalid ? __ldg(sp + j) : make_uint4(0, 0, 0, 0);
+                wd[4 * j] = q.x, wd[4 * j + 1] = q.y, wd[4 * j + 2] = q.z, wd[4 * j + 3] = q.w;
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) wd[j] = (kvalid && cc * 32 + j < nv) ? __ldg(sg + e0 + cc * 32 + j) : 0u;
+            }
+            float v[32], w[32];
+            tmem_ld32(tbase + cc * 32, v);
+            tmem_ld32(tbase + 128 + cc * 32, w);
+            tmem_ld_wait();
+            const int left = kvalid ? nv - cc * 32 : 0;  // columns of this group that are real edges
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float dp = (v[j] + w[j]) * (((wd[j] >> bitpos) & 1u) ? 1.f : 0.01f);
+              if (j < left) *prow = dp;
+              prow += ldd;
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[b]);
+        }
+      }
+    } else
     for (int item = 0; item < n_items; ++item) {
       const int net = item / (H * nhalf), h = (item / nhalf) % H, half = item % nhalf;
       const int kk = half * 128 + c;
@@ -194,6 +246,7 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
             const float dp = (v[j] + w[j]) * (((wd[j] >> bitpos) & 1u) ? 1.f : 0.01f);
             acc += dp;
             racc += dp;
+
           }
           cur = mt[cc * 32 + 31];
           currk = mt[2 * kBT + cc * 32 + 31];
@@ -470,10 +523,134 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArg
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Segment sums of the per-edge pre-activation gradients (HBM-bound; replaces the thread-sequential segment
+// sums of the dgrad epilogue and a whole second dgrad pass over source-grouped edges):
+//     pass 0  G[a, dst_off + c] = sum over the in-edges of atom a   (rows of d_pre are destination-sorted)
+//     pass 1  G[s, src_off + c] = sum over the out-edges t of atom s of d_pre[row_t, c]
+//             d_rank[chunk, r, c] = sum over the chunk's edges with shell rank r
+// One CTA = (pass, tile of 512 columns, contiguous chunk of atoms); thread = one float4 column group, sequential
+// over its atoms and edges, so every sum has a fixed order (deterministic, no atomics).  Ranks are non-decreasing
+// along an atom's out-edges, so the rank sums are run-length accumulated in registers and flushed to shared memory.
+constexpr int kSRThreads = 128;
+constexpr int kSRCols = kSRThreads * 4;
+
+struct ReducePass {
+  const int32_t* rowptr;   // (N+1) CSR of this edge order
+  const int32_t* row;      // (E) row of d_pre of each edge of this order, or null (identity)
+  const int32_t* rnk;      // (E) shell rank, or null (no per-rank sums)
+  float* d_rank;           // (n_chunks, n_ranks, cols) or null
+  int col_off;
+};
+struct ReduceArgs {
+  ReducePass pass[2];
+  const float* d_pre;
+  float* G;
+  int64_t ldd, ldg;
+  int n_atoms, n_ranks, cols, n_chunks;
+};
+
+__global__ void __launch_bounds__(kSRThreads) edge_reduce_kernel(const ReduceArgs g) {
+  extern __shared__ float4 sr_acc[];  // [n_ranks][kSRThreads]
+  const ReducePass& ps = g.pass[blockIdx.z];
+  const int tid = threadIdx.x;
+  const int col = blockIdx.x * kSRCols + tid * 4;
+  const bool active = col < g.cols;
+  const int chunk = blockIdx.y;
+  const int a_lo = (int)((int64_t)g.n_atoms * chunk / g.n_chunks);
+  const int a_hi = (int)((int64_t)g.n_atoms * (chunk + 1) / g.n_chunks);
+  const bool ranks = ps.rnk != nullptr && ps.d_rank != nullptr;
+  if (ranks)
+    for (int r = 0; r < g.n_ranks; ++r) sr_acc[r * kSRThreads + tid] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* src = g.d_pre + col;
+  float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+  int cur_rank = 0;
+  for (int a = a_lo; a < a_hi; ++a) {
+    const int b = __ldg(ps.rowptr + a), e = __ldg(ps.rowptr + a + 1);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t0 = b; t0 < e; t0 += 8) {
+      float4 v[8];
+      int rk[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        rk[j] = -1;
+        if (t0 + j < e) {
+          rk[j] = ranks ? __ldg(ps.rnk + t0 + j) : 0;
+          const int64_t r = ps.row ? __ldg(ps.row + t0 + j) : t0 + j;
+          if (active) v[j] = __ldg(reinterpret_cast<const float4*>(src + r * g.ldd));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (rk[j] < 0) continue;  // uniform across the CTA
+        acc.x += v[j].x, acc.y += v[j].y, acc.z += v[j].z, acc.w += v[j].w;
+        if (ranks) {
+          if (rk[j] != cur_rank) {  // uniform: rank runs are a property of the edge list
+            float4 s = sr_acc[cur_rank * kSRThreads + tid];
+            s.x += run.x, s.y += run.y, s.z += run.z, s.w += run.w;
+            sr_acc[cur_rank * kSRThreads + tid] = s;
+            run = make_float4(0.f, 0.f, 0.f, 0.f);
+            cur_rank = rk[j];
+          }
+          run.x += v[j].x, run.y += v[j].y, run.z += v[j].z, run.w += v[j].w;
+        }
+      }
+    }
+    if (active) *reinterpret_cast<float4*>(g.G + (int64_t)a * g.ldg + ps.col_off + col) = acc;
+  }
+  if (ranks) {
+    float4 s = sr_acc[cur_rank * kSRThreads + tid];
+    s.x += run.x, s.y += run.y, s.z += run.z, s.w += run.w;
+    sr_acc[cur_rank * kSRThreads + tid] = s;
+    if (active)
+      for (int r = 0; r < g.n_ranks; ++r)
+        *reinterpret_cast<float4*>(ps.d_rank + ((int64_t)chunk * g.n_ranks + r) * g.cols + col) =
+            sr_acc[r * kSRThreads + tid];
+  }
+}
+
 }  // namespace
 }  // namespace cgat
 
 using namespace cgat;
+
+extern "C" int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms) {
+  int64_t c = (n_atoms + 47) / 48;  // ~48 atoms per CTA; 5 column tiles x 2 passes x 60 chunks ~ 4 CTAs per SM
+  return (int32_t)(c < 1 ? 1 : (c > 60 ? 60 : c));
+}
+
+// Segment sums of the per-edge pre-activation gradients d_pre (E, cols; rows in destination order) that
+// cgat_edge_attn_dgrad wrote:  G[a, dst_col_off : +cols] = sum over the in-edges of atom a (contiguous rows
+// [dst_rowptr[a], dst_rowptr[a+1])),  G[a, src_col_off : +cols] = sum over its out-edges (rows src_row[t] for t in
+// [src_rowptr[a], src_rowptr[a+1])),  d_rank (cgat_edge_attn_reduce_chunks(N), n_ranks, cols) = per-chunk sums per
+// shell rank src_rank[t] (sum over dim 0 = dL/dT).  HBM-bound: reads d_pre twice, deterministic, no atomics.
+extern "C" int cgat_edge_attn_reduce(const float* d_pre, int64_t ldd, const int32_t* dst_rowptr,
+                                     const int32_t* src_rowptr, const int32_t* src_row, const int32_t* src_rank,
+                                     float* G, int64_t ldg, int32_t dst_col_off, int32_t src_col_off, float* d_rank,
+                                     int32_t n_ranks, int64_t n_atoms, int32_t cols, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if ((cols & 3) || (ldd & 3) || (ldg & 3) || (dst_col_off & 3) || (src_col_off & 3))
+    return fail(-2, "cgat_edge_attn_reduce: cols, ldd, ldg and the column offsets must be multiples of 4");
+  if (n_ranks < 1 || n_ranks > kBMaxRanks) return fail(-2, "cgat_edge_attn_reduce: n_ranks must be in [1,32]");
+  if (n_atoms <= 0 || cols <= 0) return 0;
+  const int n_chunks = cgat_edge_attn_reduce_chunks(n_atoms);
+  ReduceArgs a{};
+  a.pass[0] = ReducePass{dst_rowptr, nullptr, nullptr, nullptr, dst_col_off};
+  a.pass[1] = ReducePass{src_rowptr, src_row, src_rank, d_rank, src_col_off};
+  a.d_pre = d_pre, a.G = G, a.ldd = ldd, a.ldg = ldg;
+  a.n_atoms = (int)n_atoms, a.n_ranks = n_ranks, a.cols = cols, a.n_chunks = n_chunks;
+  const size_t smem = (size_t)n_ranks * kSRThreads * sizeof(float4);
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(edge_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kBMaxRanks * kSRThreads * (int)sizeof(float4)));
+    configured = true;
+  }
+  dim3 grid((unsigned)ceil_div(cols, kSRCols), (unsigned)n_chunks, 2);
+  edge_reduce_kernel<<<grid, kSRThreads, smem, stream>>>(a);
+  return check_launch("edge_reduce_kernel");
+}
 
 extern "C" int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges) {
   const int64_t tiles = ceil_div(n_edges, kBT);
@@ -483,12 +660,13 @@ extern "C" int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges) {
 // One pass of the dgrad + segment reduction.  `segptr/seg/row/rnk` describe the edge order of this pass
 // (grouped by destination or by source).  Writes G[:, col_off : col_off + 2*H*Hd]; rows of atoms without
 // edges in this order are left untouched (zero them beforehand).  d_rank (optional):
-// (cgat_edge_attn_dgrad_grid(E), n_ranks, 2*H*Hd) per-CTA partial sums per shell rank.
+// (cgat_edge_attn_dgrad_grid(E), n_ranks, 2*H*Hd) per-CTA partial sums per shell rank.  d_pre (optional, identity
+// order only): (E, 2*H*Hd) the per-edge pre-activation gradients themselves.
 extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t* signs,
                                     const int32_t* segptr, const int32_t* seg, const int32_t* row, const int32_t* rnk,
                                     const float* wt_a_packed, const float* wt_m_packed, float* G, int64_t ldg,
-                                    int32_t col_off, float* d_rank, int32_t n_ranks, int64_t n_atoms, int64_t n_edges,
-                                    int32_t heads, int32_t f, int32_t hd, void* stream_) {
+                                    int32_t col_off, float* d_rank, int32_t n_ranks, float* d_pre, int64_t n_atoms,
+                                    int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (f != kBF) return fail(-2, "cgat_edge_attn_dgrad: only F = 128 is instantiated");
   if (heads < 1 || heads > 8 || hd <= 0 || (hd & 127))
@@ -500,7 +678,8 @@ extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, con
     CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     configured = true;
   }
-  DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, ldg,
+  if (d_pre && row) return fail(-2, "cgat_edge_attn_dgrad: d_pre needs the identity edge order (row == NULL)");
+  DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, d_pre, ldg,
               col_off, (int)n_atoms, (int)n_edges, heads, hd, n_ranks};
   edge_dgrad_kernel<<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
   return check_launch("edge_dgrad_kernel");

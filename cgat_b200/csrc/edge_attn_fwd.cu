@@ -17,11 +17,14 @@
 // no per-edge intermediate ever reaches HBM, bit-reproducible.
 //
 // One persistent CTA per SM owns a contiguous range of destination atoms (hence whole softmax
-// segments), balanced by edge count.  Roles (416 threads):
-//   warps 0-3   epilogue: tcgen05.ld gate/message rows, segmented online softmax, write out[d,h,:]
-//   warps 4-11  producers: gather + LeakyReLU + split -> shared memory (B operand); the first of them also
+// segments), balanced by edge count.  Roles (800 threads):
+//   warps 0-7   epilogue, two groups of 4 warps (a warp reads the TMEM lanes 32*(warp%4)...): group g owns TMEM
+//               buffer g, i.e. every other (tile, head) item — tcgen05.ld gate/message rows, segmented softmax,
+//               write out[d,h,:].  The per-head state carried across tiles passes between the groups through
+//               shared memory + one mbarrier per head.
+//   warps 8-23  producers: gather + LeakyReLU + split -> shared memory (B operand); the first of them also
 //               issues the cp.async.bulk of the pre-packed W2 chunk (A operand); 3-stage full/empty mbarrier ring
-//   warp  12    TMEM allocation (512 columns: 2 heads x {gate, message} x 128) + single-thread MMA issue
+//   warp  24    TMEM allocation (512 columns: 2 buffers x {gate, message} x 128) + single-thread MMA issue
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -33,8 +36,9 @@ constexpr int kET = 128;             // edges per tile (MMA N)
 constexpr int kEF = 128;             // output channels per head (MMA M) — instantiated for F = 128
 constexpr int kEProducers = 512;     // producer threads; kEProducers / kEGroup groups alternate pipeline stages
 constexpr int kEGroup = 256;
-constexpr int kEMmaWarp = (128 + kEProducers) / 32;
-constexpr int kEThreads = 128 + kEProducers + 32;
+constexpr int kEEpilogue = 256;      // two groups of 128 epilogue threads
+constexpr int kEMmaWarp = (kEEpilogue + kEProducers) / 32;
+constexpr int kEThreads = kEEpilogue + kEProducers + 32;
 constexpr int kEStages = 3;
 constexpr int kEStageBytes = 2 * (int)kPackStageBytes;  // [W2 chunk hi|lo][hidden chunk hi|lo]
 constexpr int kEMaxHeads = 8;
@@ -115,7 +119,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
   uint64_t* empty = bars + kEStages;            // [3]
   uint64_t* tmem_full = bars + 2 * kEStages;    // [2]
   uint64_t* tmem_empty = tmem_full + 2;         // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* carry_bar = tmem_empty + 2;         // [kEMaxHeads] carried softmax state of head h is in shared memory
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(carry_bar + kEMaxHeads);
   int32_t* range = reinterpret_cast<int32_t*>(tmem_slot + 1);  // e_lo, e_hi
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -131,6 +136,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
       mbar_init(&tmem_full[b], 1);
       mbar_init(&tmem_empty[b], 128);
     }
+    for (int h = 0; h < kEMaxHeads; ++h) mbar_init(&carry_bar[h], 128);
     mbar_init_fence();
     // this CTA's destination-atom range: whole softmax segments, balanced by edge count
     const int G = gridDim.x;
@@ -148,12 +154,16 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
   const int e_lo = range[0], e_hi = range[1];
   const int n_tiles = (e_hi - e_lo + kET - 1) / kET;
 
-  if (warp < 4) {
+  if (warp < kEEpilogue / 32) {
     // ---------------------------------------------------------------- epilogue
     // Thread = channel (TMEM lane); it walks the tile's 128 edge columns.  Segment boundaries arrive as bit masks
-    // from the producers, so the per-column code is straight-line: the flush of a finished segment is a predicated
-    // store to an address kept ready, resets are selects, exp runs on the SFU (fast_exp).
-    const int c = warp * 32 + lane;
+    // from the producers and are warp-uniform, so "a segment ended here" is a uniform branch taken about once in
+    // max_nbr columns.  Softmax with a LAZY reference: m is the gate of the segment's first edge and is only moved
+    // (with a rescale of den / acc) when a later gate exceeds it by more than 16 — one exp per element instead of
+    // the two of the textbook online softmax; the result acc / den is the same ratio.
+    const int grp = warp >> 2;
+    const int c = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int hf = H * kEF;
     uint32_t hcount = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
@@ -163,16 +173,20 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
       const bool last_tile = (tile == n_tiles - 1);
       for (int h = 0; h < H; ++h, ++hcount) {
         const uint32_t hb = hcount & 1u;
+        if ((int)hb != grp) continue;
         float* cs = carry + (h * 4) * kEF;
         const int hc = h * kEF + c;
         const float ba = __ldg(g.b2a + hc), bm = __ldg(g.b2m + hc);
         mbar_wait(&tmem_full[hb], (hcount >> 1) & 1u);
         tc_fence_after();
-        const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + hb * 256;
+        const uint32_t tbase = tmem + lane_base + hb * 256;
         if (kMode == 0) {
           float m = -INFINITY, den = 0.f, acc = 0.f;
           int d = -1;
-          if (tile > 0) m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = __float_as_int(cs[3 * kEF + c]);
+          if (tile > 0) {
+            mbar_wait(&carry_bar[h], (uint32_t)(tile - 1) & 1u);  // written by the group that had (tile-1, h)
+            m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = __float_as_int(cs[3 * kEF + c]);
+          }
           {  // tile start: the one place that needs a compare against the carried segment
             const int d0 = mt[0];
             if (d0 != d) {
@@ -181,10 +195,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                 g.out[o] = acc / (den + g.eps);
                 if (g.smax) g.smax[o] = m, g.sden[o] = den;
               }
-              m = -INFINITY, den = 0.f, acc = 0.f, d = d0;
+              m = -INFINITY, den = 0.f, acc = 0.f;
             }
           }
-          int po = mt[3 * kET] + hc;  // offset of the open segment's output element
 #pragma unroll 1
           for (int cc = 0; cc < kET / 16; ++cc) {
             float av[16], vv[16];
@@ -196,21 +209,21 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int t = cc * 16 + j;
-              const bool sf = (sflags >> j) & 1u;  // edge t opens a new segment: flush the finished one
-              const float q = acc * fast_rcp(den + g.eps);
-              if (sf) g.out[po] = q;
-              if (sf && g.smax != nullptr) g.smax[po] = m, g.sden[po] = den;
-              m = sf ? -INFINITY : m;
-              den = sf ? 0.f : den;
-              acc = sf ? 0.f : acc;
-              po = mt[3 * kET + t] + hc;
+              if ((sflags >> j) & 1u) {  // edge t opens a new segment: flush the finished one (never at t = 0)
+                const int po = mt[3 * kET + t - 1] + hc;
+                g.out[po] = acc * fast_rcp(den + g.eps);
+                if (g.smax != nullptr) g.smax[po] = m, g.sden[po] = den;
+                m = -INFINITY, den = 0.f, acc = 0.f;
+              }
               const float a = ((valid >> j) & 1u) ? av[j] + ba : -INFINITY;  // padding columns contribute exp(-inf) = 0
               const float v = vv[j] + bm;
-              const float mn = fmaxf(m, a);
-              const float r = fast_exp(m - mn), p = fast_exp(a - mn);
-              den = fmaf(den, r, p);
-              acc = fmaf(acc, r, p * v);
-              m = mn;
+              if (a - m > 16.f) {  // first edge of a segment (m = -inf), or a rare much larger gate
+                const float r = fast_exp(m - a);
+                den *= r, acc *= r, m = a;
+              }
+              const float p = fast_exp(a - m);
+              den += p;
+              acc = fmaf(p, v, acc);
             }
           }
           d = mt[nv - 1];
@@ -222,6 +235,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             if (g.smax) g.smax[o] = m, g.sden[o] = den;
           } else {
             cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc, cs[3 * kEF + c] = __int_as_float(d);
+            mbar_arrive(&carry_bar[h]);
           }
         } else {
           float* pg = g.d_gate + (int64_t)e0 * hf + hc;
@@ -259,7 +273,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     }
   } else if (warp < kEMmaWarp) {
     // ---------------------------------------------------------------- producers
-    const int pt = tid - 128;
+    const int pt = tid - kEEpilogue;
     const uint32_t grp = (uint32_t)pt >> 8;  // stage cnt is produced by group (cnt & 1)
     const int pl = pt & (kEGroup - 1);
     uint32_t cnt = 0;

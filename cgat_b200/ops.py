@@ -459,20 +459,26 @@ class _EdgeAttentionFused(torch.autograd.Function):
                   _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(g), _lib.ptr(d_gate),
                   _lib.ptr(d_msg), _lib.ptr(signs), n, e, heads, f, hd, 1e-16, st,
                   work=dict(key="edge_attn_bwd_prep", bound="tensor", flops=flops2))
-        # 2. dgrad + segment sums, edges grouped by destination then by source
-        d_p = torch.zeros((n, 4 * hhd), dtype=torch.float32, device=dev)
+        # 2. dgrad on the tensor cores -> per-edge d_pre, then its per-destination / per-source / per-rank sums
+        #    (HBM-bound, cgat_edge_attn_reduce)
         wt_a, wt_m = _w2_transposed_packed(w2a, heads), _w2_transposed_packed(w2m, heads)
         n_ranks = tab.shape[0]
-        grid = int(lib.cgat_edge_attn_dgrad_grid(e))
-        d_rank = torch.zeros((grid, n_ranks, 2 * hhd), dtype=torch.float32, device=dev)
-        wk = dict(key="edge_attn_dgrad", bound="tensor", flops=flops2)
+        d_pre = torch.empty((e, 2 * hhd), dtype=torch.float32, device=dev)
         _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(plan.rowptr),
-                  _lib.ptr(plan.dst), None, None, _lib.ptr(wt_a), _lib.ptr(wt_m), _lib.ptr(d_p), 4 * hhd, 0, None,
-                  n_ranks, n, e, heads, f, hd, st, work=wk)
+                  _lib.ptr(plan.dst), None, None, _lib.ptr(wt_a), _lib.ptr(wt_m), None, 4 * hhd, 0, None,
+                  n_ranks, _lib.ptr(d_pre), n, e, heads, f, hd, st,
+                  work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2))
         so = plan.by_source()
-        _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(so.rowptr),
-                  _lib.ptr(so.seg), _lib.ptr(so.row), _lib.ptr(so.rank), _lib.ptr(wt_a), _lib.ptr(wt_m), _lib.ptr(d_p),
-                  4 * hhd, 2 * hhd, _lib.ptr(d_rank), n_ranks, n, e, heads, f, hd, st, work=wk)
+        chunks = int(lib.cgat_edge_attn_reduce_chunks(n))
+        d_p = torch.empty((n, 4 * hhd), dtype=torch.float32, device=dev)
+        d_rank = torch.empty((chunks, n_ranks, 2 * hhd), dtype=torch.float32, device=dev)
+        _lib.call("cgat_edge_attn_reduce", _lib.ptr(d_pre), 2 * hhd, _lib.ptr(plan.rowptr), _lib.ptr(so.rowptr),
+                  _lib.ptr(so.row), _lib.ptr(so.rank), _lib.ptr(d_p), 4 * hhd, 0, 2 * hhd, _lib.ptr(d_rank), n_ranks,
+                  n, 2 * hhd, st,
+                  work=dict(key="edge_attn_reduce", bound="hbm",
+                            bytes=4.0 * (2 * e * 2 * hhd + n * 4 * hhd + chunks * n_ranks * 2 * hhd),
+                            note="reads d_pre twice (by destination, by source), writes dL/dP + per-rank partials"))
+        del d_pre
         d_t = d_rank.sum(dim=0)                                                     # (K+1, 2*HHd)
         # 3. second-layer weight / bias gradients
         splits = int(lib.cgat_edge_attn_wgrad_splits(heads))

@@ -162,9 +162,10 @@ int cgat_hyper_wgrad(const float* g, const float* y, const float* z, float* out,
 /* ---- fused edge attention, backward -------------------------------------
  * Step 1: recompute a, v; write d_gate = dL/da, d_msg = dL/dv (E,H,F; destination-sorted rows) and the
  *         LeakyReLU sign masks signs[2][H][ceil(Hd/32)][E].  g_out = dL/d out (N,H,F).
- * Step 2 (run once per edge grouping: by destination, by source): d_hid = dZ W2 on the tensor cores,
- *         d_pre = d_hid * leaky_relu'(pre), G[seg, col_off + ...] = per-segment sums (= dL/dP blocks), and
- *         optionally per-rank partial sums d_rank (grid, n_ranks, 2*H*Hd) (= dL/dT after summing dim 0).
+ * Step 2: d_hid = dZ W2 on the tensor cores, d_pre = d_hid * leaky_relu'(pre), G[seg, col_off + ...] =
+ *         per-segment sums (= dL/dP blocks); optionally per-rank partial sums d_rank (grid, n_ranks, 2*H*Hd)
+ *         — or, with d_pre != NULL (identity order only), just the per-edge d_pre (E, 2*H*Hd), whose segment
+ *         sums cgat_edge_attn_reduce takes (G and d_rank are then not written).
  *         wt_*_packed: cgat_pack_kmajor of W2^T per head, shape (H*Hd, F).
  * Step 3: dL/dW2 = dZ^T hid, contraction over edges with MN-major operands; partial results
  *         (cgat_edge_attn_wgrad_splits(H), 2, H, F, Hd).
@@ -179,8 +180,19 @@ int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges);
 int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t* signs, const int32_t* segptr,
                          const int32_t* seg, const int32_t* row, const int32_t* rnk, const float* wt_a_packed,
                          const float* wt_m_packed, float* G, int64_t ldg, int32_t col_off, float* d_rank,
-                         int32_t n_ranks, int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd,
-                         void* stream);
+                         int32_t n_ranks, float* d_pre, int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f,
+                         int32_t hd, void* stream);
+/* Segment sums of the per-edge pre-activation gradients d_pre (E, cols; destination-sorted rows) written by
+ * cgat_edge_attn_dgrad(d_pre != NULL): HBM-bound, deterministic, replaces the segment sums of the dgrad epilogue
+ * and a second tensor-core pass over source-grouped edges.
+ *   G[a, dst_col_off:+cols] = sum over the in-edges of atom a;  G[a, src_col_off:+cols] = sum over its out-edges
+ *   (src_rowptr / src_row / src_rank: the source-grouped order, src_row = row of d_pre);
+ *   d_rank (cgat_edge_attn_reduce_chunks(N), n_ranks, cols): partial sums per shell rank (sum dim 0 = dL/dT). */
+int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms);
+int cgat_edge_attn_reduce(const float* d_pre, int64_t ldd, const int32_t* dst_rowptr, const int32_t* src_rowptr,
+                          const int32_t* src_row, const int32_t* src_rank, float* G, int64_t ldg,
+                          int32_t dst_col_off, int32_t src_col_off, float* d_rank, int32_t n_ranks, int64_t n_atoms,
+                          int32_t cols, void* stream);
 int32_t cgat_edge_attn_wgrad_splits(int32_t heads);
 int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
                          const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
