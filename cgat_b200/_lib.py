@@ -29,17 +29,19 @@ SIGNATURES = {
     "cgat_seg_softmax_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F32,
                                             _P, _P, _P]),
     "cgat_gemm3x_nt": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I64, _I64, _I32, _P]),
+    "cgat_gemm3x_nt_res": (ctypes.c_int, [_P, _I64, _P, _P, _P, _I64, _I64, _I64, _I64, _I32, _P]),
+    "cgat_gemm3x_nt_splitk": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _I32, _P]),
     "cgat_gemm3x_tn": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _I32, _P]),
     "cgat_packed_floats": (_I64, [_I64, _I64]),
     "cgat_pack_kmajor": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
-    "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_trunk_packed_floats": (_I64, [_I32, _I32]),
     "cgat_hyper_trunk_pack": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),
     "cgat_hyper_trunk_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "cgat_hyper_trunk_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "cgat_gemm3x_tn_batched": (ctypes.c_int, [_P, _P, _I32, _I64, _I64, _P, _P, _I64, _I64, _I64, _I32, _P]),
     "cgat_hyper_rowscale_parts": (_I32, [_I64, _I32]),
-    "cgat_hyper_rowscale": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_rowscale": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_wgrad_splits": (_I32, [_I64]),
     "cgat_hyper_wgrad": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_edge_attn_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,

@@ -241,28 +241,29 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           float* pg = g.d_gate + (int64_t)e0 * hf + hc;
           float* pm = g.d_msg + (int64_t)e0 * hf + hc;
 #pragma unroll 1
-          for (int cc = 0; cc < kET / 16; ++cc) {
-            float av[16], vv[16];
-            tmem_ld16(tbase + cc * 16, av);
-            tmem_ld16(tbase + 128 + cc * 16, vv);
-            tmem_ld_wait();
-            const uint32_t valid = ((uint32_t)mt[4 * kET + 4 + (cc >> 1)]) >> ((cc & 1) * 16);
+          for (int cc = 0; cc < kET / 8; ++cc) {
             // per-segment statistics re-read per column: same address for the ~max_nbr edges of a segment, so these
-            // are L1 hits; it keeps the column code free of branches and of load-latency bubbles
-            float sm[16], sd[16], so[16], sg_[16];
+            // are L1 hits; it keeps the column code free of branches.  8 columns per batch: 32 loads in flight and
+            // everything stays in registers under the 80-register cap of an 800-thread CTA
+            float sm[8], sd[8], so[8], sg_[8];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int o = mt[3 * kET + cc * 16 + j] + hc;
+            for (int j = 0; j < 8; ++j) {
+              const int o = mt[3 * kET + cc * 8 + j] + hc;
               sm[j] = __ldg(g.smax + o), sd[j] = __ldg(g.sden + o), so[j] = __ldg(g.out + o), sg_[j] = __ldg(g.g_out + o);
             }
+            float av[8], vv[8];
+            tmem_ld8(tbase + cc * 8, av);
+            tmem_ld8(tbase + 128 + cc * 8, vv);
+            tmem_ld_wait();
+            const uint32_t valid = ((uint32_t)mt[4 * kET + 4 + (cc >> 2)]) >> ((cc & 3) * 8);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
+            for (int j = 0; j < 8; ++j) {
               const float a = av[j] + ba, v = vv[j] + bm;
               const float alpha = fast_exp(a - sm[j]) * fast_rcp(sd[j] + g.eps);
               const float ag = alpha * sg_[j];
               if ((valid >> j) & 1u) {
-                pm[(int64_t)(cc * 16 + j) * hf] = ag;
-                pg[(int64_t)(cc * 16 + j) * hf] = ag * (v - so[j]);
+                pm[(int64_t)(cc * 8 + j) * hf] = ag;
+                pg[(int64_t)(cc * 8 + j) * hf] = ag * (v - so[j]);
               }
             }
           }

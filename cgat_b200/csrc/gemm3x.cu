@@ -73,7 +73,8 @@ __device__ __forceinline__ void stage_chunk(const float* __restrict__ src, int64
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restrict__ B, int64_t ldb,
-                 const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int act) {
+                 const float* __restrict__ bias, float* __restrict__ C, int64_t ldc, int M, int N, int K, int act,
+                 int k_per_split, int64_t split_stride) {
   using S = GemmSmem<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base_u32 = smem_u32(smem_raw);
@@ -86,7 +87,11 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.y * kBM, n0 = blockIdx.x * BN;
-  const int nk = (K + kKC - 1) / kKC;
+  // split-K over blockIdx.z: partial products `split_stride` floats apart (bias / act only with one split)
+  const int k_begin = blockIdx.z * k_per_split;
+  const int k_end = min(K, k_begin + k_per_split);
+  const int nk = (k_end - k_begin + kKC - 1) / kKC;
+  C += (int64_t)blockIdx.z * split_stride;
 
   if (tid == 0) {
     for (int s = 0; s < S::kStages; ++s) {
@@ -110,8 +115,8 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       const int s = kc % S::kStages, u = kc / S::kStages;
       mbar_wait(&empty[s], (u + 1) & 1);  // passes immediately on the first use of a stage
       uint8_t* st = smem + s * S::kStageBytes;
-      stage_chunk<kBM>(A, lda, m0, M, kc * kKC, K, st, st + S::kABytes, tid);
-      stage_chunk<BN>(B, ldb, n0, N, kc * kKC, K, st + 2 * S::kABytes, st + 2 * S::kABytes + S::kBBytes, tid);
+      stage_chunk<kBM>(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + S::kABytes, tid);
+      stage_chunk<BN>(B, ldb, n0, N, k_begin + kc * kKC, k_end, st + 2 * S::kABytes, st + 2 * S::kABytes + S::kBBytes, tid);
       fence_async_smem();
       mbar_arrive(&full[s]);
     }
@@ -331,15 +336,17 @@ gemm3x_tn_kernel(const TnArgs g) {
 
 template <int BN>
 int launch_gemm(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C, int64_t ldc,
-                int M, int N, int K, int act, cudaStream_t stream) {
+                int M, int N, int K, int act, cudaStream_t stream, int n_split = 1, int64_t split_stride = 0) {
   using S = GemmSmem<BN>;
   static bool configured = false;
   if (!configured) {
     CGAT_CUDA(cudaFuncSetAttribute(gemm3x_nt_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kBytes));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, kBM));
-  gemm3x_nt_kernel<BN><<<grid, kThreads, S::kBytes, stream>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, act);
+  int k_per_split = (int)ceil_div(ceil_div(K, n_split), kKC) * kKC;
+  dim3 grid((unsigned)ceil_div(N, BN), (unsigned)ceil_div(M, kBM), (unsigned)n_split);
+  gemm3x_nt_kernel<BN><<<grid, kThreads, S::kBytes, stream>>>(A, lda, B, ldb, bias, C, ldc, M, N, K, act, k_per_split,
+                                                              split_stride);
   return check_launch("gemm3x_nt_kernel");
 }
 
@@ -381,6 +388,22 @@ int check_tn(const float* A, const float* B, int64_t lda, int64_t ldb, int64_t M
   return 0;
 }
 }  // namespace
+
+// Split-K form of cgat_gemm3x_nt for long contractions with few output tiles (dL/dx = dP W1: K = 4*H*Hd):
+// C[s][M,N] = A[:, split s of K] * B[:, split s of K]^T, partial results `split_stride` floats apart.
+extern "C" int cgat_gemm3x_nt_splitk(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                                     int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split,
+                                     void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M <= 0 || N <= 0 || n_split <= 0) return 0;
+  if (K <= 0 || (K & 3) || (lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(A) & 15) ||
+      (reinterpret_cast<uintptr_t>(B) & 15))
+    return fail(-2, "cgat_gemm3x_nt_splitk: K, lda, ldb must be multiples of 4 and A, B 16-byte aligned");
+  if (M >= (1ll << 31) || N >= (1ll << 31) || K >= (1ll << 31)) return fail(-2, "cgat_gemm3x_nt_splitk: size overflow");
+  if (N <= 64)
+    return launch_gemm<64>(A, lda, B, ldb, nullptr, C, ldc, (int)M, (int)N, (int)K, 0, stream, n_split, split_stride);
+  return launch_gemm<128>(A, lda, B, ldb, nullptr, C, ldc, (int)M, (int)N, (int)K, 0, stream, n_split, split_stride);
+}
 
 // C[split][M,N] = sum over this split's rows k of A[k,m] * B[k,n].  n_split partial results, `split_stride`
 // floats apart (the caller sums them: keeps the K/8-step accumulation short and fills the SMs).

@@ -11,11 +11,12 @@
 //     e[n,o] = sum_i bl[o*F+i] y_in[n,i] + sum_k Wl[F*F+o,k] z[n,k] + bl[F*F+o]
 // is a plain (N x 2F) x (2F x F) product computed beforehand by cgat_gemm3x_nt and added here.
 //
-// Roles (288 threads, one persistent CTA per SM):
-//   warps 0-3  epilogue: y_in row in registers, tcgen05.ld + FMA row-dot, store y_out
-//   warps 4-7  stage the z tile (fp32 -> tf32 hi/lo, SWIZZLE_128B K-major); warp 4 lane 0 then streams the
-//              pre-packed weight stages with cp.async.bulk (32 KB each) through a 3-deep mbarrier ring
-//   warp  8    TMEM allocation + single-thread MMA issue
+// Roles (416 threads, one persistent CTA per SM):
+//   warps 0-7   epilogue, two groups of four warps, each owning half of the accumulator columns: half a y_in row in
+//               registers, tcgen05.ld + FMA row-dot, store y_out
+//   warps 8-11  stage the z tile (fp32 -> tf32 hi/lo, SWIZZLE_128B K-major); warp 8 lane 0 then streams the
+//               pre-packed weight stages with cp.async.bulk (32 KB each) through a 3-deep mbarrier ring
+//   warp  12    TMEM allocation + single-thread MMA issue
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -30,7 +31,7 @@ struct HyperCfg {
   static constexpr int kStages = 3;                             // 128 KB z tile (hi+lo) + 3 x 32 KB weight stages = 224 KB
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + 1024 + kBarBytes;
-  static constexpr int kThreads = 288;
+  static constexpr int kThreads = 416;
   // two buffers x (main, correction) accumulators.  The tensor core truncates the fp32 accumulator on
   // every MMA; keeping the 2^-11-sized lo*hi / hi*lo terms in their own accumulator means the large
   // hi*hi sum sees K/8 truncations instead of 3K/8, and the two are added once, rounded to nearest.
@@ -45,8 +46,8 @@ struct HyperCfg {
 template <int F, int kMode>
 __global__ void __launch_bounds__(HyperCfg<F>::kThreads, 1)
 hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
-                        const float* __restrict__ e_term2, const float* __restrict__ w_packed,
-                        float* __restrict__ y_out, int n_atoms, int oc) {
+                        const float* __restrict__ e_term2, const float* __restrict__ w_bias,
+                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
   using Cfg = HyperCfg<F>;
   static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
   extern __shared__ uint8_t smem_raw[];
@@ -78,32 +79,40 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
-      mbar_init(&tmem_empty[b], 128);
+      mbar_init(&tmem_empty[b], 256);
     }
     mbar_init(a_full, 128);
     mbar_init(a_free, 1);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  if (warp == 12) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < 8) {
     // ------------------------------------------------------------------ epilogue
+    // Two groups of four warps (a warp reads the TMEM lanes 32*(warp%4)...): group g owns columns [64g, 64g+64) of
+    // every accumulator, so a thread keeps half a row (64 registers) and the per-tile epilogue time is halved — it,
+    // not the MMAs, was pacing the kernel.  kMode 0: the two half dot products of an output meet in y_out itself
+    // (group 1 stores its half, a named barrier, group 0 adds its own + the e term); kMode 1 needs no exchange.
+    constexpr int HF = F / 2;
+    const int grp = warp >> 2;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ocount = 0;
     for (int item = item_lo; item < item_hi; ++item) {
       const int tile = item / n_chunks, chunk = item - tile * n_chunks;
-      const int n = tile * 128 + warp * 32 + lane;
+      const int n = tile * 128 + (warp & 3) * 32 + lane;
       const bool valid = n < n_atoms;
-      float y[F];  // kMode 0: this atom's y_in row; kMode 1: the running partial sums over o
+      float y[HF];  // kMode 0: this atom's half y_in row; kMode 1: the running partial sums over o
 #pragma unroll
-      for (int j = 0; j < F / 4; ++j) {
+      for (int j = 0; j < HF / 4; ++j) {
         float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F) + j);
+        if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * HF) + j);
         y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
       }
+      float accs[16];  // kMode 0: half dot products of this item's <= 16 outputs
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
         const int o = chunk * oc + oi;
         const uint32_t b = ocount & 1u;
@@ -111,12 +120,23 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
         mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
         tc_fence_after();
         float acc = 0.f;
+        const uint32_t tb = tmem + lane_base + b * 2 * F + grp * HF;
 #pragma unroll
-        for (int cc = 0; cc < F / 16; ++cc) {
+        for (int cc = 0; cc < HF / 16; ++cc) {
           float v[16], w[16];
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + cc * 16, v);
-          tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + b * 2 * F + F + cc * 16, w);
+          tmem_ld16(tb + cc * 16, v);
+          tmem_ld16(tb + F + cc * 16, w);
           tmem_ld_wait();
+          if (w_bias != nullptr) {
+            // bias of the predicted weight row: p[n, o*F + j] = D_o[n, j] + bl[o*F + j] (same address for every
+            // thread: broadcast loads), so neither forward nor dL/dy needs a separate (N x F) x (F x F) product
+            const float4* bp = reinterpret_cast<const float4*>(w_bias + (int64_t)o * F + grp * HF + cc * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = __ldg(bp + q);
+              w[4 * q] += b4.x, w[4 * q + 1] += b4.y, w[4 * q + 2] += b4.z, w[4 * q + 3] += b4.w;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             if (kMode == 0) acc = fmaf(v[j] + w[j], y[cc * 16 + j], acc);
@@ -125,21 +145,37 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
         }
         tc_fence_before();
         mbar_arrive(&tmem_empty[b]);
-        if (kMode == 0 && valid) {
-          float e = __ldg(e_term + (int64_t)n * F + o);
-          if (e_term2 != nullptr) e += __ldg(e_term2 + (int64_t)n * F + o);
-          y_out[(int64_t)n * F + o] = acc + e;
+        if (kMode == 0) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q == oi) accs[q] = acc;  // static indexing keeps accs in registers
+        }
+      }
+      if (kMode == 0) {
+        float* yo = y_out + (int64_t)n * F + chunk * oc;
+        if (grp == 1 && valid) {
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q < oc) yo[q] = accs[q];
+        }
+        asm volatile("bar.sync 2, 256;" ::: "memory");  // both epilogue groups; orders the global stores above
+        if (grp == 0 && valid) {
+          const float* e1 = e_term + (int64_t)n * F + chunk * oc;
+          const float* e2 = e_term2 ? e_term2 + (int64_t)n * F + chunk * oc : nullptr;
+#pragma unroll
+          for (int q = 0; q < 16; ++q)
+            if (q < oc) yo[q] = (accs[q] + __ldcg(yo + q)) + (__ldg(e1 + q) + (e2 ? __ldg(e2 + q) : 0.f));
         }
       }
       if (kMode == 1 && valid) {
-        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F);
+        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F + grp * HF);
 #pragma unroll
-        for (int j = 0; j < F / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        for (int j = 0; j < HF / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 12) {
     // ------------------------------------------------------------------ z-tile stagers + weight TMA
-    const int st = tid - 128;  // 0..127
+    const int st = tid - 256;  // 0..127
     uint32_t it = 0, cnt = 0;
     int staged_tile = -1;
     for (int item = item_lo; item < item_hi; ++item) {
@@ -232,7 +268,7 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == 12) {
     tc_fence_after();
     tmem_dealloc(tmem, Cfg::kTmemCols);
   }
@@ -253,8 +289,8 @@ int hyper_chunk(int64_t n_atoms, int f) {
 }
 
 template <int kMode>
-int launch_hyper(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_packed,
-                 float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {
+int launch_hyper(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
+                 const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {
   if (n_atoms <= 0) return 0;
   if (f != 128) return fail(-2, "cgat_hyper_*: only F = 128 is instantiated");
   if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_*: too many atoms");
@@ -270,26 +306,30 @@ int launch_hyper(const float* z, const float* y_in, const float* e_term, const f
   const int n_items = n_tiles * (f / oc);
   const int grid = n_items < kNumSMs ? n_items : kNumSMs;
   hyper_rowdot_fwd_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_packed, y_out, (int)n_atoms, oc);
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc);
   return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");
 }
 }  // namespace
 
-// y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) y_in[n,i] + e_term[n,o]
+// y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k] + w_bias[o*F+i]) y_in[n,i] + e_term[n,o]   (w_bias optional)
 //   z, y_in, e_term, e_term2 (optional, added to e_term), y_out: (n_atoms, F) fp32 contiguous;
 //   w_packed: cgat_pack_kmajor of W[:F*F, :F]
 extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* e_term2,
-                                     const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, void* stream_) {
-  return launch_hyper<0>(z, y_in, e_term, e_term2, w_packed, y_out, n_atoms, f, (cudaStream_t)stream_);
+                                     const float* w_bias, const float* w_packed, float* y_out, int64_t n_atoms,
+                                     int32_t f, void* stream_) {
+  if (w_bias && (reinterpret_cast<uintptr_t>(w_bias) & 15)) return fail(-2, "cgat_hyper_rowdot_fwd: w_bias must be 16-byte aligned");
+  return launch_hyper<0>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, f, (cudaStream_t)stream_);
 }
 
 // number of partial results cgat_hyper_rowscale writes for this problem size
 extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { return f / hyper_chunk(n_atoms, f); }
 
-// partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m]);  sum over c = the result.
+// partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m] + w_bias[o*F+j]);  sum over c = the
+// result (w_bias optional: the bias of the predicted weights when a = z, NULL when a = y).
 //   a, scale: (n_atoms, F); w_packed: cgat_pack_kmajor of the F blocks Wblk_o (F x F each, stacked);
 //   partial: (cgat_hyper_rowscale_parts, n_atoms, F)
-extern "C" int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_packed, float* partial,
-                                   int64_t n_atoms, int32_t f, void* stream_) {
-  return launch_hyper<1>(a, scale, nullptr, nullptr, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
+extern "C" int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_bias, const float* w_packed,
+                                   float* partial, int64_t n_atoms, int32_t f, void* stream_) {
+  if (w_bias && (reinterpret_cast<uintptr_t>(w_bias) & 15)) return fail(-2, "cgat_hyper_rowscale: w_bias must be 16-byte aligned");
+  return launch_hyper<1>(a, scale, nullptr, nullptr, w_bias, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
 }

@@ -2,9 +2,9 @@
 
 The reference reaches the same thing through pytorch-lightning's DDP strategy (reference
 CGAT/train.py:53-63, default 'ddp').  Crystals are independent units, so the only
-collective is the gradient sum.  All live gradients are views into ONE flat fp32 buffer, which makes
-the exchange a single in-place all-reduce (NVLS-capable, 249 MB at the default config) and lets
-zero_grad be one memset.  Parameters that never receive a gradient (the reference's dead Edge
+collective is the gradient sum.  The live gradients are packed into ONE flat fp32 buffer, which makes
+the exchange a single in-place all-reduce (NVLS-capable, 249 MB at the default config); zero_grad just
+drops the gradients, so backward writes them without accumulate kernels.  Parameters that never receive a gradient (the reference's dead Edge
 attention and the last layer's edge update — 44 tensors) are excluded from the buffer,
 mirroring DDP's find_unused_parameters behaviour.
 """
@@ -30,23 +30,30 @@ def live_parameters(model):
 
 
 class GradSync:
+    """zero_grad() drops the gradients (autograd then stores each one without an accumulate kernel);
+    all_reduce() packs the live gradients into ONE flat fp32 buffer, exchanges it with a single in-place
+    all-reduce and leaves every p.grad as a view into that buffer (no copy back)."""
+
     def __init__(self, model, world_size=1, process_group=None):
         self.world, self.group = world_size, process_group
         self.params = [p for _, p in live_parameters(model) if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
-        dev = self.params[0].device
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
-            n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
-            off += n
+        self.sizes = [p.numel() for p in self.params]
+        self.flat = None
+        if world_size > 1:
+            self.flat = torch.zeros(sum(self.sizes), dtype=torch.float32, device=self.params[0].device)
+        self.zero_grad()
 
     def zero_grad(self):
-        self.flat.zero_()
+        for p in self.params:
+            p.grad = None
 
     def all_reduce(self):
         """Sum over ranks and divide by world size (DDP semantics). No-op for a single rank."""
-        if self.world > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-            self.flat.div_(self.world)
+        if self.world <= 1:
+            return
+        grads = [p.grad.reshape(-1) if p.grad is not None else torch.zeros_like(p).reshape(-1) for p in self.params]
+        torch.cat(grads, out=self.flat)
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(self.world)
+        for p, v in zip(self.params, self.flat.split(self.sizes)):
+            p.grad = v.view_as(p)

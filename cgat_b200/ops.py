@@ -139,6 +139,35 @@ def gemm3x(a, w, bias=None, act=0, out=None):
     return out
 
 
+def gemm3x_res(a, w_packed, n_out, bias=None, act=0):
+    """act(a @ w.T + bias) for K <= 128 against a wide pre-packed weight (cgat_gemm3x_nt_res):
+    a (M,K) row-contiguous, w_packed = packed_kmajor of w (n_out, K)."""
+    M, K = a.shape
+    if a.stride(1) != 1 or not a.is_cuda:
+        raise ValueError("gemm3x_res needs a row-contiguous CUDA operand")
+    out = torch.empty((M, n_out), dtype=torch.float32, device=a.device)
+    _lib.call("cgat_gemm3x_nt_res", a.data_ptr(), a.stride(0), _lib.ptr(w_packed), _lib.ptr(bias), out.data_ptr(),
+              n_out, M, n_out, K, act, _lib.stream(),
+              work=dict(key="gemm3x_nt_res", bound="tensor", flops=2.0 * M * n_out * K,
+                        bytes=4.0 * (M * K + M * n_out)))
+    return out
+
+
+def gemm3x_splitk(a, w, n_split=None):
+    """a @ w.T for a long contraction with few output tiles (cgat_gemm3x_nt_splitk): a (M,K), w (N,K)."""
+    M, K = a.shape
+    N = w.shape[0]
+    if a.stride(1) != 1 or w.stride(1) != 1 or not a.is_cuda:
+        raise ValueError("gemm3x_splitk needs row-contiguous CUDA operands")
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if n_split is None:
+        n_split = max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+    part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
+    _lib.call("cgat_gemm3x_nt_splitk", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), part.data_ptr(), N, M * N,
+              M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))
+    return part[0] if n_split == 1 else part.sum(dim=0)
+
+
 def gemm3x_tn(a, b, n_split=None):
     """a.T @ b on the tensor cores (cgat_gemm3x_tn): a (K,M), b (K,N) row-contiguous -> (M,N).  The
     weight-gradient shape: contraction over the rows (atoms / edges) of both operands."""
@@ -188,19 +217,18 @@ class _HyperLinear(torch.autograd.Function):
         z, y = _f32c(z), _f32c(y)
         n, f = y.shape
         ff = f * f
+        bias = bias.contiguous()
+        ctx.has_e = e is not None
         if e is None:
-            # bias-shaped remainder: e = [y | z] @ [bl.view(F,F) | W[F*F:]]^T + bl[F*F:]
-            we = torch.cat([bias[:ff].view(f, f), weight[ff:]], dim=1)
-            e1, e2 = gemm3x(torch.cat([y, z], dim=1), we, bias[ff:].contiguous()), None
-        else:
-            e1, e2 = _f32c(e), gemm3x(y, bias[:ff].view(f, f))
+            # bias tail of the last Linear: e = z W[F*F:]^T + b[F*F:] (the fused trunk kernel supplies it otherwise)
+            e = gemm3x(z, weight[ff:], bias[ff:])
         out = torch.empty_like(y)
-        _lib.call("cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y), _lib.ptr(e1), _lib.ptr(e2), _lib.ptr(w_packed),
-                  _lib.ptr(out), n, f, _lib.stream(),
+        # the bias of the predicted weights, b[:F*F], is added inside the kernel's epilogue
+        _lib.call("cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y), _lib.ptr(_f32c(e)), None, _lib.ptr(bias),
+                  _lib.ptr(w_packed), _lib.ptr(out), n, f, _lib.stream(),
                   work=dict(key="hyper_rowdot_fwd", bound="tensor", flops=2.0 * n * f * ff,
                             note="3xTF32: 3 tensor passes per algorithmic flop"))
         ctx.save_for_backward(z, weight, bias, y, w_packed, w_packed_bt)
-        ctx.has_e = e is not None
         return out
 
     @staticmethod
@@ -213,13 +241,14 @@ class _HyperLinear(torch.autograd.Function):
         work = dict(key="hyper_rowscale", bound="tensor", flops=2.0 * n * f * ff,
                     note="3xTF32: 3 tensor passes per algorithmic flop")
         # dL/dy[n,i] = sum_o g[n,o] (W z[n] + b)[o*F+i]: recomputed tile by tile on the tensor cores
+        bias = bias.contiguous()
         buf = torch.empty((parts, n, f), dtype=torch.float32, device=y.device)
-        _lib.call("cgat_hyper_rowscale", _lib.ptr(z), _lib.ptr(g), _lib.ptr(w_packed), _lib.ptr(buf), n, f,
-                  _lib.stream(), work=work)
-        g_y = buf.sum(dim=0) + gemm3x(g, bias[:ff].view(f, f).t().contiguous())
+        _lib.call("cgat_hyper_rowscale", _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed), _lib.ptr(buf),
+                  n, f, _lib.stream(), work=work)
+        g_y = buf.sum(dim=0)
         # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ the bias-tail rows unless they went through `e`)
         buf2 = torch.empty_like(buf)
-        _lib.call("cgat_hyper_rowscale", _lib.ptr(y), _lib.ptr(g), _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
+        _lib.call("cgat_hyper_rowscale", _lib.ptr(y), _lib.ptr(g), None, _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
                   _lib.stream(), work=work)
         g_z = buf2.sum(dim=0)
         if not ctx.has_e:
@@ -396,6 +425,28 @@ def _w2_transposed_packed(w2, heads):
     return buf
 
 
+def _first_layer_operands(w1a, w1m, b1a, b1m, f, fe):
+    """Regrouped first-layer weights of the gate / message MLPs: per-atom block (4*HHd, F) =
+    [W1A_i; W1M_i; W1A_j; W1M_j] (+ its packed image), per-rank block (2*HHd, Fe) = [W1A_e; W1M_e] and the
+    concatenated bias.  Cached on the weight and keyed by the autograd versions, so screening inference builds
+    them once and training once per optimizer step."""
+    key = tuple((t._version, t.data_ptr()) for t in (w1a, w1m, b1a, b1m))
+    cache = w1a.__dict__.setdefault("_cgat_first_layer", {})
+    if cache.get("key") == key:
+        return cache["val"]
+    hhd = w1a.shape[0]
+    w1a2, w1m2 = w1a.detach().view(hhd, -1), w1m.detach().view(hhd, -1)
+    w_atom = torch.cat([w1a2[:, :f], w1m2[:, :f], w1a2[:, f + fe:], w1m2[:, f + fe:]], dim=0)       # (4*HHd, F)
+    w_rank = torch.cat([w1a2[:, f:f + fe], w1m2[:, f:f + fe]], dim=0)                               # (2*HHd, Fe)
+    b1 = torch.cat([b1a.detach(), b1m.detach()])
+    lib = _lib.load()
+    packed = torch.empty(int(lib.cgat_packed_floats(4 * hhd, f)), dtype=torch.float32, device=w1a.device)
+    _lib.call("cgat_pack_kmajor", _lib.ptr(w_atom), w_atom.stride(0), 4 * hhd, f, 0, _lib.ptr(packed), _lib.stream(),
+              work=dict(key="pack_kmajor", bound="hbm", bytes=12.0 * 4 * hhd * f))
+    cache["key"], cache["val"] = key, (w_atom, packed, w_rank, b1, w_atom.t().contiguous())
+    return cache["val"]
+
+
 class _EdgeAttentionFused(torch.autograd.Function):
     """Forward: per-atom / per-rank first-layer projections (cgat_gemm3x_nt) + the fused gather /
     second-layer MMA / segmented-softmax kernel (cgat_edge_attn_fwd).  No per-edge tensor is written.
@@ -410,11 +461,9 @@ class _EdgeAttentionFused(torch.autograd.Function):
         fe = edge_table.shape[1]
         hhd = w1a.shape[0]
         hd = hhd // heads
-        w1a2, w1m2 = w1a.view(hhd, -1), w1m.view(hhd, -1)
-        w_atom = torch.cat([w1a2[:, :f], w1m2[:, :f], w1a2[:, f + fe:], w1m2[:, f + fe:]], dim=0)   # (4*HHd, F)
-        w_rank = torch.cat([w1a2[:, f:f + fe], w1m2[:, f:f + fe]], dim=0)                           # (2*HHd, Fe)
-        P = gemm3x(x, w_atom)                                                                        # (N, 4*HHd)
-        T = gemm3x(edge_table, w_rank, torch.cat([b1a, b1m]))                                        # (K+1, 2*HHd)
+        w_atom, w_atom_packed, w_rank, b1, w_atom_t = _first_layer_operands(w1a, w1m, b1a, b1m, f, fe)
+        P = gemm3x_res(x, w_atom_packed, 4 * hhd)                                                    # (N, 4*HHd)
+        T = gemm3x(edge_table, w_rank, b1)                                                           # (K+1, 2*HHd)
         train = any(ctx.needs_input_grad)
         out = torch.empty((n, heads, f), dtype=torch.float32, device=x.device)
         smax = torch.empty_like(out) if train else None
@@ -430,13 +479,13 @@ class _EdgeAttentionFused(torch.autograd.Function):
                             note="second MLP layer (E x Hd x F per head, gate+message) on tcgen05, 3xTF32"))
         if train:
             ctx.save_for_backward(x, edge_table, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax,
-                                  sden, w_atom, w_rank)
+                                  sden, w_atom_t, w_rank)
             ctx.plan, ctx.heads = plan, heads
         return out
 
     @staticmethod
     def backward(ctx, g):
-        (x, tab, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax, sden, w_atom,
+        (x, tab, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax, sden, w_atom_t,
          w_rank) = ctx.saved_tensors
         plan, heads = ctx.plan, ctx.heads
         n, f = x.shape
@@ -490,7 +539,7 @@ class _EdgeAttentionFused(torch.autograd.Function):
         g_w2a, g_w2m = d_w2[0].reshape(w2a.shape), d_w2[1].reshape(w2m.shape)
         g_b2a, g_b2m = d_gate.sum(dim=0).reshape(-1), d_msg.sum(dim=0).reshape(-1)
         # 4. first layer: P = x w_atom^T, T = tab w_rank^T + b1
-        g_x = gemm3x(d_p, w_atom.t().contiguous())
+        g_x = gemm3x_splitk(d_p, w_atom_t)
         g_watom = gemm3x_tn(d_p, x)                                                 # (4*HHd, F)
         g_tab = d_t @ w_rank
         g_wrank = d_t.t() @ tab                                                     # (2*HHd, Fe)

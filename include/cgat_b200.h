@@ -77,6 +77,17 @@ int cgat_seg_softmax_bwd(const float* gate, const float* value, const float* u, 
 int cgat_gemm3x_nt(const float* A, int64_t lda, const float* B, int64_t ldb, const float* bias, float* C,
                    int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act, void* stream);
 
+/* Persistent form for a SHORT contraction (K <= 128) against a WIDE pre-packed weight — the per-atom
+ * first-layer projections P = x [W1A_i; W1M_i; W1A_j; W1M_j]^T (reference CGAT/CGAT.py:103-109, 320-322):
+ * w_packed = cgat_pack_kmajor(W, ld, N, K, 0); the A tile stays resident, accumulators are double-buffered.  */
+int cgat_gemm3x_nt_res(const float* A, int64_t lda, const float* w_packed, const float* bias, float* C,
+                       int64_t ldc, int64_t M, int64_t N, int64_t K, int32_t act, void* stream);
+
+/* Split-K form for long contractions with few output tiles (dL/dx = dL/dP * W1, K = 4*H*Hd): n_split partial
+ * products `split_stride` floats apart, no bias / activation; the caller sums them.                 */
+int cgat_gemm3x_nt_splitk(const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+                          int64_t split_stride, int64_t M, int64_t N, int64_t K, int32_t n_split, void* stream);
+
 /* C[s][M,N] = sum_{k in split s} A[k,m] * B[k,n]  (A [K x M], B [K x N] row-major): the weight-gradient
  * shape dW = dY^T X of every nn.Linear / Conv1d(k=1) backward on this path.  Operands are staged
  * MN-major (no transposed copies).  n_split partial results `split_stride` floats apart.          */
@@ -100,13 +111,15 @@ int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_
                      void* stream);
 
 /* ---- fused hypernetwork linear layer ----------------------------------
- * y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k]) * y_in[n,i] + e_term[n,o]
+ * y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k] + w_bias[o*F+i]) * y_in[n,i] + e_term[n,o]
  * Replaces Linear(F -> F*F+F) + view + BatchLinear (reference CGAT/Hypernetworksmp.py:243-254,
  * 205-209) without materialising the (N, F*F+F) predicted-weight tensor.  w_packed =
- * cgat_pack_kmajor(W[:F*F,:F]); e_term (+ optional e_term2, may be NULL) carry the bias-shaped
+ * cgat_pack_kmajor(W[:F*F,:F]); w_bias (optional) = the first F*F entries of the Linear's bias, added to
+ * the predicted weights in the epilogue; e_term (+ optional e_term2, may be NULL) carry the bias-shaped
  * remainder (see hyper_fwd.cu).                                                                   */
 int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const float* e_term, const float* e_term2,
-                          const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, void* stream);
+                          const float* w_bias, const float* w_packed, float* y_out, int64_t n_atoms, int32_t f,
+                          void* stream);
 
 /* ---- fused hypernetwork trunks -------------------------------------------
  * The J (<= 4) HyperLinears of a node layer share the hyper-input h; each runs
@@ -143,13 +156,14 @@ int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, co
                        int32_t f, int32_t hd, float eps, void* stream);
 
 /* Backward companion of cgat_hyper_rowdot_fwd (activation gradients):
- *   partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m]);  result = sum_c partial[c]
+ *   partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m] + w_bias[o*F+j]);  result =
+ *   sum_c partial[c]   (w_bias optional: pass the Linear's bias with a = z, NULL with a = y)
  * (a = z, blocks of W)            -> dL/dy_in[n,i] = sum_o g[n,o] * (W z + ..)[o,i]
  * (a = y, transposed blocks of W) -> dL/dz[n,k]    = sum_o g[n,o] * sum_i y[n,i] W[o*F+i,k]
  * partial holds cgat_hyper_rowscale_parts(n_atoms, f) x n_atoms x f floats.                      */
 int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f);
-int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_packed, float* partial,
-                        int64_t n_atoms, int32_t f, void* stream);
+int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_bias, const float* w_packed,
+                        float* partial, int64_t n_atoms, int32_t f, void* stream);
 
 /* Weight gradient of the hyper-linear layer: dL/dW[o*F+i, k] = sum_n g[n,o] y[n,i] z[n,k], contracted over
  * atoms with MN-major operands; the scaled rows g[n,o]*y[n,:] are formed while staging (the reference's

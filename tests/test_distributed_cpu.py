@@ -28,14 +28,16 @@ def _worker(rank, world, port):
     x = torch.full((3, 4), float(rank + 1))
     loss = model.out(model.graphs[0]["Node"](x)).sum() + model.graphs[0]["Edge"]["Pooling_NN"](torch.ones(3)).sum()
     loss.backward()
-    local = sync.flat.clone()
+    # parameters that took no part in this step (graphs.1.Node here) enter the exchange as zeros
+    local = torch.cat([p.grad.reshape(-1) if p.grad is not None else torch.zeros(p.numel()) for p in sync.params])
     sync.all_reduce()
     gathered = [torch.zeros_like(local) for _ in range(world)]
     dist.all_gather(gathered, local)
     assert torch.allclose(sync.flat, sum(gathered) / world)
     assert model.out.weight.grad.data_ptr() >= sync.flat.data_ptr()  # grads are views of the flat buffer
+    assert torch.allclose(model.out.weight.grad.reshape(-1), sync.flat[-5:-1])
     sync.zero_grad()
-    assert float(model.out.weight.grad.abs().sum()) == 0.0
+    assert all(p.grad is None for p in sync.params)
     dist.destroy_process_group()
 
 

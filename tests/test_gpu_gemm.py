@@ -72,3 +72,35 @@ def test_gemm3x_tn_matches_fp64(K, M, N, split):
     rel = ((c.double() - ref).abs() / bound).max().item()
     print(f"gemm3x_tn {K}x{M}x{N}: max err / sum|a||b| = {rel:.3e}")
     assert rel <= 3e-7 + 2e-7 * (K / 8) ** 0.5, f"max err / sum|a||b| = {rel:.3e}"
+
+
+@pytest.mark.parametrize("M,N,K,act", [(1, 128, 128, 0), (119, 5120, 128, 0), (5559, 5120, 128, 0), (300, 200, 96, 1),
+                                       (700, 384, 128, 2), (129, 130, 4, 3)])
+def test_gemm3x_res_matches_fp64(M, N, K, act):
+    """cgat_gemm3x_nt_res (persistent, resident A tile, packed weight) against an fp64 product."""
+    from cgat_b200 import ops
+    g = torch.Generator().manual_seed(M * 13 + N * 5 + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = torch.randn(N, K, generator=g).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    c = ops.gemm3x_res(a, ops.packed_kmajor(w), N, bias, act)
+    pre = a.double() @ w.double().t() + bias.double()
+    ref = [pre, torch.nn.functional.leaky_relu(pre, 0.01), torch.tanh(pre), torch.relu(pre)][act]
+    bound = a.double().abs() @ w.double().abs().t() + bias.double().abs()
+    rel = ((c.double() - ref).abs() / bound).max().item()
+    limit = 3e-7 + 2e-7 * (K / 8) ** 0.5
+    assert rel <= limit, f"max err / sum|a||b| = {rel:.3e} (limit {limit:.3e})"
+
+
+@pytest.mark.parametrize("M,N,K", [(5559, 128, 5120), (100, 128, 640), (300, 64, 2000)])
+def test_gemm3x_splitk_matches_fp64(M, N, K):
+    from cgat_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn(M, K, generator=g).to(DEV)
+    w = torch.randn(N, K, generator=g).to(DEV)
+    c = ops.gemm3x_splitk(a, w)
+    ref = a.double() @ w.double().t()
+    bound = a.double().abs() @ w.double().abs().t()
+    rel = ((c.double() - ref).abs() / bound).max().item()
+    limit = 3e-7 + 2e-7 * (3 * K / 8) ** 0.5
+    assert rel <= limit, f"max err / sum|a||b| = {rel:.3e} (limit {limit:.3e})"
