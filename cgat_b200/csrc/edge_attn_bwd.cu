@@ -616,8 +616,10 @@ __global__ void __launch_bounds__(kSRThreads) edge_reduce_kernel(const ReduceArg
 using namespace cgat;
 
 extern "C" int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms) {
-  int64_t c = (n_atoms + 47) / 48;  // ~48 atoms per CTA; 5 column tiles x 2 passes x 60 chunks ~ 4 CTAs per SM
-  return (int32_t)(c < 1 ? 1 : (c > 60 ? 60 : c));
+  // ~24 atoms per CTA: every CTA walks its atoms one after the other (index load -> row loads -> store), so the
+  // memory-level parallelism comes from the number of resident CTAs (8+ per SM at 27 KB of shared memory each)
+  int64_t c = (n_atoms + 23) / 24;
+  return (int32_t)(c < 1 ? 1 : (c > 240 ? 240 : c));
 }
 
 // Segment sums of the per-edge pre-activation gradients d_pre (E, cols; rows in destination order) that
@@ -691,6 +693,8 @@ extern "C" int32_t cgat_edge_attn_wgrad_splits(int32_t heads) {
 }
 
 // out: (cgat_edge_attn_wgrad_splits(H), 2, H, F, Hd) partial dL/dW2 (gate net, message net); sum over dim 0.
+// (Passing the hidden activations from the backward-prep kernel instead of re-gathering them was measured: slower,
+// the re-gather hits P in L2 while a saved (E, 2*H*Hd) copy comes back from HBM.)
 extern "C" int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
                                     const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
                                     int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream_) {

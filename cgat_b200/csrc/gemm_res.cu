@@ -94,9 +94,13 @@ gemm3x_nt_res_kernel(const float* __restrict__ A, int64_t lda, const float* __re
         const int nb = nt * 128 + cc * 32;
         if (m < M) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const float bj = (bias != nullptr && nb + j < N) ? __ldg(bias + nb + j) : 0.f;
-            v[j] = res_act((v[j] + w[j]) + bj, act);
+          for (int j = 0; j < 32; ++j) v[j] += w[j];
+          if (bias != nullptr || act != 0) {  // kept out of the common path: the inlined activations are large
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float bj = (bias != nullptr && nb + j < N) ? __ldg(bias + nb + j) : 0.f;
+              v[j] = res_act(v[j] + bj, act);
+            }
           }
           float* crow = C + (int64_t)m * ldc + nb;
           if (vec_ok && nb + 32 <= N) {
@@ -160,7 +164,7 @@ gemm3x_nt_res_kernel(const float* __restrict__ A, int64_t lda, const float* __re
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_tf32(128, 128);
+    constexpr uint32_t idesc = umma_idesc_tf32(128, 128), idesc2 = umma_idesc_tf32(128, 256);
     uint32_t it = 0, cnt = 0, tc = 0;
     int staged = -1;
     for (int item = item_lo; item < item_hi; ++item, ++tc) {
@@ -181,12 +185,14 @@ gemm3x_nt_res_kernel(const float* __restrict__ A, int64_t lda, const float* __re
           const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
           const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes), b_lo = b_hi + kPackImageBytes;
           const uint32_t d = tmem + b * 256, dc = d + 128;
+          (void)b_lo;
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
+            // one N = 256 MMA against the adjacent [hi | lo] weight images: a_hi*b_hi -> [d, d+128), a_hi*b_lo ->
+            // [d+128, d+256); then a_lo*b_hi into the correction columns (see hyper_fwd.cu)
             const uint32_t off = ks * 32;
-            umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-            umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-            umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+            umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+            umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
           }
           umma_commit(&empty[s]);
           if (kc == kcn - 1) umma_commit(&tmem_full[b]);

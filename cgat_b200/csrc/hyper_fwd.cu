@@ -226,7 +226,7 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_tf32(128, F);
+    constexpr uint32_t idesc = umma_idesc_tf32(128, F), idesc2 = umma_idesc_tf32(128, 2 * F);
     uint32_t it = 0, cnt = 0, ocount = 0;
     int staged_tile = -1;
     for (int item = item_lo; item < item_hi; ++item) {
@@ -249,12 +249,17 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
             const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
             const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes), b_lo = b_hi + kPackImageBytes;
             const uint32_t d = tmem + b * 2 * F, dc = d + F;
+            // The hi and lo images of a weight stage are adjacent, so ONE N = 2F MMA multiplies a_hi with both:
+            // columns [d, d+F) receive a_hi*b_hi (main), [d+F, d+2F) a_hi*b_lo (correction); a second N = F MMA adds
+            // a_lo*b_hi to the correction columns.  Two instructions and 20 KB of shared-memory operand reads per
+            // K step instead of three and 24 KB — with M = N = 128 operand tiles the SS-mode MMAs run at the
+            // shared-memory bandwidth limit, not at the tensor pipe's.
+            (void)b_lo;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
-              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-              umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
             }
             umma_commit(&empty[s]);
             if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);
