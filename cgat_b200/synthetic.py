@@ -37,24 +37,25 @@ class GraphBatch:
     """Duck-type of torch_geometric's Batch: the attributes CGAtNet.forward reads
     (reference CGAT/CGAT.py:566-571)."""
 
-    def __init__(self, x, edge_index, edge_attr, batch, y=None):
+    def __init__(self, x, edge_index, edge_attr, batch, y=None, num_graphs=None):
         self.x, self.edge_index, self.edge_attr, self.batch, self.y = x, edge_index, edge_attr, batch, y
+        # a host-side int like torch_geometric's Batch.num_graphs (known at collation time): reading it from the
+        # device tensor would be a device->host sync in every forward (the reference has one at CGAT/CGAT.py:52)
+        if num_graphs is None:
+            num_graphs = int(batch[-1]) + 1 if batch.numel() else 0
+        self.num_graphs = num_graphs
 
     @property
     def num_nodes(self):
         return self.x.shape[0]
 
-    @property
-    def num_graphs(self):
-        return int(self.batch[-1]) + 1 if self.batch.numel() else 0
-
     def to(self, device, non_blocking=False):
         f = lambda t: None if t is None else t.to(device, non_blocking=non_blocking)
-        return GraphBatch(f(self.x), f(self.edge_index), f(self.edge_attr), f(self.batch), f(self.y))
+        return GraphBatch(f(self.x), f(self.edge_index), f(self.edge_attr), f(self.batch), f(self.y), self.num_graphs)
 
     def pin_memory(self):
         f = lambda t: None if t is None else t.pin_memory()
-        return GraphBatch(f(self.x), f(self.edge_index), f(self.edge_attr), f(self.batch), f(self.y))
+        return GraphBatch(f(self.x), f(self.edge_index), f(self.edge_attr), f(self.batch), f(self.y), self.num_graphs)
 
     def tensors(self):
         return [t for t in (self.x, self.edge_index, self.edge_attr, self.batch, self.y) if t is not None]
