@@ -217,9 +217,32 @@ def run_ours(args):
     print(json.dumps(line))
 
 
+KERNEL_NAMES = {  # profile key (ops.py `work`) -> kernel name in the ncu capture (profiles/*_kernel_metrics.json)
+    "hyper_rowscale": "hyper_rowdot_fwd_kernel<128, 1>", "hyper_rowdot_fwd": "hyper_rowdot_fwd_kernel<128, 0>",
+    "hyper_wgrad": "hyper_wgrad_kernel", "hyper_trunk_fwd": "hyper_trunk_kernel<0>",
+    "hyper_trunk_bwd": "hyper_trunk_kernel<1>", "edge_attn_fwd": "edge_attn_kernel<0>",
+    "edge_attn_bwd_prep": "edge_attn_kernel<1>", "edge_attn_dgrad": "edge_dgrad_kernel",
+    "edge_attn_wgrad": "edge_wgrad_kernel", "edge_attn_reduce": "edge_reduce_kernel",
+    "gemm3x_nt": "gemm3x_nt_kernel<128>", "gemm3x_nt_res": "gemm3x_nt_res_kernel", "gemm3x_tn": "gemm3x_tn_kernel",
+    "gemm3x_tn_batched": "gemm3x_tn_kernel",
+}
+
+
+def ncu_traffic(key, workload):
+    """dram bytes (read + write) per launch of this kernel from the committed `ncu --set full` capture of the same
+    workload (profiles/<round>_<workload>_kernel_metrics.json, written by scripts/ncu_metrics.py), else None."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_{workload}_kernel_metrics.json")))
+    if not files:
+        return None, None
+    m = json.load(open(files[-1])).get(KERNEL_NAMES.get(key, key))
+    return (m["traffic_bytes"], os.path.relpath(files[-1], ROOT)) if m else (None, None)
+
+
 def roofline(model, sb, tgt, train, step, args):
-    """Per-launch CUDA-event timing of this library's kernels over extra (untimed) steps; reports the
-    kernel with the largest share.  Algorithmic bytes / flops per launch are declared by the ops."""
+    """Per-launch CUDA-event timing of this library's kernels over extra (untimed) steps, on the stream they are
+    launched on; reports the kernel with the largest share of the step.  Algorithmic bytes / flops per launch are
+    declared by the ops (cgat_b200/ops.py `work=`) and stated in DESIGN.md."""
     from cgat_b200 import _lib
     pk = peaks()
     _lib.profile_begin()
@@ -239,11 +262,20 @@ def roofline(model, sb, tgt, train, step, args):
     else:
         achieved = top["bytes"] / top["launches"] / (avg_ms * 1e-3) / 1e9
         peak, unit = pk["hbm"], "GB/s"
-    return {"kernel": name, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
-            "frac": round(achieved / peak, 4), "traffic": None, "peak_source": pk["source"],
-            "avg_launch_ms": round(avg_ms, 5), "share_of_own_kernel_time": round(top["ms"] / total, 4),
-            "own_kernels_ms_per_step": round(total / n, 4),
-            "note": top.get("note", "")}
+    traffic, traffic_src = ncu_traffic(name, args.workload)
+    shares = {k: round(v["ms"] / total, 4) for k, v in sorted(rows.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+    out = {"kernel": name, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
+           "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
+           "peak_source": pk["source"] + (" (bf16 dense, sustained)" if bound == "tensor" else " (copy bandwidth)"),
+           "avg_launch_ms": round(avg_ms, 5), "launches_per_step": top["launches"] // n,
+           "share_of_own_kernel_time": round(top["ms"] / total, 4),
+           "own_kernels_ms_per_step": round(total / n, 4), "own_kernel_shares": shares,
+           "note": top.get("note", "")}
+    if bound == "tensor":
+        # fp32 parity needs three TF32 passes per product: the same launch as tensor-pipe work
+        out["tf32_pass_tflops"] = round(3 * achieved, 2)
+        out["frac_of_3xtf32_ceiling"] = round(3 * achieved / (pk["bf16_sustained"] / 2), 4)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
