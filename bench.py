@@ -99,9 +99,13 @@ def make_pool(wl, rank, n=4):
             for i in range(n)]
 
 
-def target_norm(sb, dev):
+def target_norm(sb, dev, n_real=None):
+    """Normalised targets of the real crystals (a padded batch carries one dummy crystal at the end: target 0)."""
     y = sb.graph.y
-    return ((y - y.mean()) / (y.std() + 1e-6)).view(-1, 1).to(dev)
+    n_real = y.shape[0] if n_real is None else n_real
+    t = torch.zeros_like(y)
+    t[:n_real] = (y[:n_real] - y[:n_real].mean()) / (y[:n_real].std() + 1e-6)
+    return t.view(-1, 1).to(dev)
 
 
 def run_ours(args):
@@ -121,29 +125,48 @@ def run_ours(args):
     model, net_kw = build_net(wl)
     model = model.to(dev)
     train = wl["train"]
+    use_graph = not args.no_graph
     pool = make_pool(wl, rank)
+    if use_graph:
+        # whole-step CUDA graphs need bucketed shapes: one dummy crystal pads every batch (cgat_b200/batching.py)
+        from cgat_b200 import batching, graphed
+        pool = [batching.pad_batch(sb) for sb in pool]
     dev_pool = [sb.to(dev) for sb in pool]
     pin_pool = [sb.pin_memory() for sb in pool]
-    targets = [target_norm(sb, dev) for sb in pool]
+    targets = [target_norm(sb, dev, wl["crystals"]) for sb in pool]
     sync = cdist.GradSync(model, world) if train else None
-    opt = torch.optim.AdamW([p for p in model.parameters()], lr=LR, weight_decay=WD, fused=True) if train else None
+    opt = torch.optim.AdamW([p for p in model.parameters()], lr=LR, weight_decay=WD, fused=True,
+                            capturable=use_graph) if train else None
     crit = torch.nn.L1Loss()
+    n_real = wl["crystals"]
 
     def step(sb, tgt):
+        """One eager step (also what the graphs capture, via graphed.GraphedTrainStep._body)."""
         if train:
             out = model(sb.graph, sb.roost)
-            loss = crit(out[:, :1], tgt)                     # reference lightning_module.py:237-240
+            loss = crit(out[:n_real, :1], tgt[:n_real])      # reference lightning_module.py:237-240
             loss.backward()
             sync.all_reduce()
             opt.step()
             sync.zero_grad()
             return loss
         with torch.no_grad():
-            return model(sb.graph, sb.roost)
+            return model(sb.graph, sb.roost)[:n_real]
+
+    runner = None
+    if use_graph:
+        runner = graphed.GraphedTrainStep(model, opt, crit, sync) if train else graphed.GraphedForward(model)
+
+    def run(sb, tgt):
+        if runner is None:
+            return step(sb, tgt)
+        return runner.step(sb, tgt) if train else runner(sb)
 
     def e2e_step(i):
-        sb = pin_pool[i % len(pin_pool)].to(dev, non_blocking=True)
-        res = step(sb, targets[i % len(pool)])
+        sb = pin_pool[i % len(pin_pool)]
+        if runner is None:
+            sb = sb.to(dev, non_blocking=True)
+        res = run(sb, targets[i % len(pool)])               # graph mode: pinned host -> the graph's static buffers
         return float(res) if train else res[:, 0].cpu()     # device -> host read of the step's result
 
     def timed(fn, steps):
@@ -161,15 +184,19 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
-    resident = lambda i: step(dev_pool[i % len(pool)], targets[i % len(pool)])
+    resident = lambda i: run(dev_pool[i % len(pool)], targets[i % len(pool)])
+    if runner is not None:
+        # untimed preparation, like a compile step: one eager step, then one capture per distinct bucket of the pool
+        for i in range(len(pool) + 1):
+            resident(i)
     for i in range(args.warmup):
         resident(i)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + (runner.replayed_launches if runner else 0)
     ms = timed(resident, args.steps)
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() + (runner.replayed_launches if runner else 0) - l0
     clocks = sampler.stop() if rank == 0 else None
     for i in range(min(args.warmup, 2)):
         e2e_step(i)
@@ -183,6 +210,9 @@ def run_ours(args):
 
     roof = cpu = None
     if rank == 0:
+        if runner is not None and train:
+            for p in model.parameters():
+                p.grad = None                                 # the graphs own their gradient buffers
         roof = roofline(model, dev_pool[0], targets[0], train, step, args)
         if not args.no_cpu_baseline:
             cpu = cpu_baseline(wl, net_kw, train)
@@ -191,7 +221,13 @@ def run_ours(args):
         dist.destroy_process_group()
     if rank != 0:
         return
-    n_atoms = int(sum(int(sb.n_atoms.sum()) for sb in pool) / len(pool))
+    n_atoms = int(sum(int(sb.n_atoms[:n_real].sum()) for sb in pool) / len(pool))
+    graph_cfg = None
+    if runner is not None:
+        graph_cfg = {"captures": runner.captures, "buckets_atoms_elems_pairs": list(batching.DEFAULT_BUCKETS),
+                     "padded_atoms": int(sum(sb.graph.x.shape[0] for sb in pool) / len(pool)),
+                     "note": "one whole-step graph per shape bucket (forward, loss, backward, all-reduce, AdamW); "
+                             "batches padded with one dummy crystal; throughput counts real crystals only"}
     line = {
         "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),
         "value": round(value, 2), "unit": "crystals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -206,7 +242,7 @@ def run_ours(args):
                    "crystals_per_gpu": wl["crystals"], "max_nbr": wl["max_nbr"],
                    "l2": "rotating pool of 4 distinct batches; per-step working set (249 MB weights + 498 MB AdamW "
                          "state + >1 GB activations) exceeds the 126 MB L2",
-                   "parallelism": f"dp{world}" if train else f"shard{world}"},
+                   "parallelism": f"dp{world}" if train else f"shard{world}", "cuda_graph": graph_cfg},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": "crystals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e / args.steps, 4)},
@@ -375,6 +411,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_train", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
+                    "one captured CUDA graph per shape bucket")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

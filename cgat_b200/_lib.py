@@ -34,6 +34,10 @@ SIGNATURES = {
     "cgat_gemm3x_tn": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _I64, _I64, _I64, _I64, _I64, _I32, _P]),
     "cgat_packed_floats": (_I64, [_I64, _I64]),
     "cgat_pack_kmajor": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
+    "cgat_packed_floats_f16": (_I64, [_I64, _I64]),
+    "cgat_pack_kmajor_f16": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
+    "cgat_hyper_rowdot_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_rowscale_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_trunk_packed_floats": (_I64, [_I32, _I32]),
     "cgat_hyper_trunk_pack": (ctypes.c_int, [_P, _P, _I32, _I32, _I32, _P, _P]),

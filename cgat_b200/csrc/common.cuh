@@ -40,4 +40,13 @@ constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
+// hyper-linear kernels: output channels per work item — smaller chunks when there are few atom tiles, so that all
+// SMs get work (shared by the tf32 and f16 forms: cgat_hyper_rowscale_parts sizes the partial buffer of both)
+inline int hyper_chunk(int64_t n_atoms, int f) {
+  const int n_tiles = (int)((n_atoms + 127) / 128);
+  int oc = 16;
+  while (oc > 4 && (int64_t)n_tiles * (f / oc) < 3 * kNumSMs) oc >>= 1;
+  return oc;
+}
+
 }  // namespace cgat

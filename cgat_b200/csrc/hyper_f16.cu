@@ -1,0 +1,326 @@
+// Fused hypernetwork linear layer on kind::f16 tensor-core passes ("f16x3", tc_common.cuh) — same arithmetic,
+// roles and pipeline as hyper_fwd.cu (reference CGAT/Hypernetworksmp.py:243-254 HyperLinear.forward
+// + :205-209 BatchLinear), with both MMA operands (the z / y activation tile and the pre-packed Linear weight) as
+// scaled fp16 hi/lo pairs instead of tf32 hi/lo pairs:
+//   * the same 22 significand bits per operand (parity bar unchanged: tests/test_gpu_kernels.py runs both forms),
+//   * kind::f16 issues twice the flops per instruction of kind::tf32 for the same 32-byte K slab, so the operand bytes
+//     read from shared memory per flop — the resource that paces the M = N = 128 SS-mode MMAs — halve,
+//   * the z tile needs 64 KB instead of 128 KB of shared memory, which pays for a 4-stage weight ring (was 3) and
+//     the forward's 32 KB cross-group reduction buffer,
+//   * with the MMAs twice as fast the epilogue (one tcgen05.ld + FMA per accumulator element) paces the kernel
+//     (ncu r01c: tensor pipe 33 % active, epilogue warps stalled on tcgen05.ld latency), so it runs on SIXTEEN warps:
+//     4 lane quadrants x 4 groups of 32 accumulator columns, 32 live row values per thread,
+//   * the packed weight image (L2-resident, streamed once per atom tile) is 8.4 MB instead of 16.8 MB.
+// Operands here are activations (tanh / LayerNorm outputs, aggregated messages) and weights; the gradient-operand
+// kernels (hyper_wgrad, edge dgrad / wgrad) stay on tf32, whose 8-bit exponent needs no scaling.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cgat {
+namespace {
+using namespace tc;
+
+template <int F>
+struct Hyper16Cfg {
+  static constexpr int kKC = F / kPackChunk16;                  // K chunks of 64 halves (one 128-byte swizzled row)
+  static constexpr int kABytes = kKC * (int)kPackStageBytes;    // activation tile, hi+lo per chunk: 64 KB
+  static constexpr int kStages = 4;                             // 32 KB weight stages
+  static constexpr int kRedBytes = 4 * 16 * 128 * 4;            // forward: [column group][output of the item][atom row]
+  static constexpr int kBarBytes = 512;
+  static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + kRedBytes + 1024 + kBarBytes;
+  static constexpr int kEpiWarps = 16;                          // 4 column groups x 4 lane quadrants
+  static constexpr int kEpiThreads = kEpiWarps * 32;
+  static constexpr int kThreads = kEpiThreads + 128 + 32;       // + stagers + MMA warp
+  static constexpr int kTmemCols = 4 * F;                       // two buffers x (main, correction)
+};
+
+// kMode 0 (forward):   y_out[n,o] = sum_j D_o[n,j] * y_in[n,j] + e_term[n,o]
+// kMode 1 (backward):  partial[chunk][n,j] = sum_{o in chunk} y_in[n,o] * D_o[n,j]
+//   D_o[n,j] = sum_m z[n,m] Wblk_o[j,m] (+ w_bias[o*F+j]);  see hyper_fwd.cu for the two backward uses.
+template <int F, int kMode>
+__global__ void __launch_bounds__(Hyper16Cfg<F>::kThreads, 1)
+hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
+                        const float* __restrict__ e_term2, const float* __restrict__ w_bias,
+                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
+  using Cfg = Hyper16Cfg<F>;
+  static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* a_smem = smem;                                   // [kKC][hi|lo][16 KB]
+  uint8_t* b_smem = smem + Cfg::kABytes;                    // [kStages][hi|lo][16 KB]
+  float* red = reinterpret_cast<float*>(b_smem + Cfg::kStages * kPackStageBytes);  // [4][16][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(red) + Cfg::kRedBytes);
+  uint64_t* full = bars;                                    // [kStages] TMA -> MMA
+  uint64_t* empty = bars + Cfg::kStages;                    // [kStages] MMA -> TMA
+  uint64_t* tmem_full = bars + 2 * Cfg::kStages;            // [2] MMA -> epilogue
+  uint64_t* tmem_empty = tmem_full + 2;                     // [2] epilogue -> MMA
+  uint64_t* a_full = tmem_empty + 2;                        // stagers -> MMA
+  uint64_t* a_free = a_full + 1;                            // MMA -> stagers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_tiles = (n_atoms + 127) / 128;
+  const int n_chunks = F / oc;
+  const int n_items = n_tiles * n_chunks;
+  // work item = (atom tile, chunk of output channels), chunk fastest; contiguous item range per CTA
+  const int item_lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x);
+  const int item_hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
+
+  if (tid == 0) {
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full[b], 1);
+      mbar_init(&tmem_empty[b], Cfg::kEpiThreads);
+    }
+    mbar_init(a_full, 128);
+    mbar_init(a_free, 1);
+    mbar_init_fence();
+  }
+  constexpr int kMmaWarp = Cfg::kEpiWarps + 4;
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, Cfg::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < Cfg::kEpiWarps) {
+    // ------------------------------------------------------------------ epilogue
+    // 16 warps: a warp reads the TMEM lanes 32*(warp%4)..; column group grp = warp/4 owns columns [32 grp, 32 grp + 32)
+    // of every accumulator, so a thread keeps a quarter of its atom's row.  kMode 0: the four partial dot products of
+    // an output meet in shared memory (red[grp][output][row], conflict-free) and are summed, together with the e
+    // term, by all 512 threads once per work item; kMode 1 needs no exchange.
+    constexpr int QF = F / 4;
+    const int grp = warp >> 2;
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    uint32_t ocount = 0;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int tile = item / n_chunks, chunk = item - tile * n_chunks;
+      const int n = tile * 128 + row;
+      const bool valid = n < n_atoms;
+      float y[QF];  // kMode 0: this atom's quarter y_in row; kMode 1: the running partial sums over o
+#pragma unroll
+      for (int j = 0; j < QF / 4; ++j) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * QF) + j);
+        y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+      }
+      for (int oi = 0; oi < oc; ++oi, ++ocount) {
+        const int o = chunk * oc + oi;
+        const uint32_t b = ocount & 1u;
+        const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
+        mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
+        tc_fence_after();
+        float acc = 0.f;
+        const uint32_t tb = tmem + lane_base + b * 2 * F + grp * QF;
+#pragma unroll
+        for (int cc = 0; cc < QF / 8; ++cc) {
+          // 8 columns per batch: with 21 warps per CTA a thread has 80 registers, 32 of them hold the row values
+          float v[8], w[8];
+          tmem_ld8(tb + cc * 8, v);
+          tmem_ld8(tb + F + cc * 8, w);
+          tmem_ld_wait();
+          // w = (hi*lo + lo*hi products) * 2^11: rescale; + the bias of the predicted weight row (broadcast loads)
+          if (w_bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(w_bias + (int64_t)o * F + grp * QF + cc * 8);
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              const float4 b4 = __ldg(bp + q);
+              w[4 * q] = fmaf(w[4 * q], kF16LoInv, b4.x), w[4 * q + 1] = fmaf(w[4 * q + 1], kF16LoInv, b4.y);
+              w[4 * q + 2] = fmaf(w[4 * q + 2], kF16LoInv, b4.z), w[4 * q + 3] = fmaf(w[4 * q + 3], kF16LoInv, b4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] *= kF16LoInv;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            if (kMode == 0) acc = fmaf(v[j] + w[j], y[cc * 8 + j], acc);
+            else y[cc * 8 + j] = fmaf(v[j] + w[j], sc, y[cc * 8 + j]);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tmem_empty[b]);
+        if (kMode == 0) red[(grp * 16 + oi) * 128 + row] = acc;
+      }
+      if (kMode == 0) {
+        asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kEpiThreads) : "memory");  // all partials of this item are in `red`
+        // thread -> (atom row, 4 consecutive outputs of the item): y_out = (p0 + p1) + (p2 + p3) + e
+        const int q0 = grp * 4;
+        if (q0 < oc && valid) {
+          float r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float* pr = red + (q0 + q) * 128 + row;
+            r[q] = (pr[0] + pr[16 * 128]) + (pr[2 * 16 * 128] + pr[3 * 16 * 128]);
+          }
+          const int64_t off = (int64_t)n * F + chunk * oc + q0;
+          const float4 e1 = __ldg(reinterpret_cast<const float4*>(e_term + off));
+          float4 e2 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (e_term2 != nullptr) e2 = __ldg(reinterpret_cast<const float4*>(e_term2 + off));
+          *reinterpret_cast<float4*>(y_out + off) =
+              make_float4(r[0] + (e1.x + e2.x), r[1] + (e1.y + e2.y), r[2] + (e1.z + e2.z), r[3] + (e1.w + e2.w));
+        }
+        asm volatile("bar.sync 3, %0;" ::"n"(Cfg::kEpiThreads) : "memory");  // `red` may be overwritten by the next item
+      }
+      if (kMode == 1 && valid) {
+        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F + grp * QF);
+#pragma unroll
+        for (int j = 0; j < QF / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+      }
+    }
+  } else if (warp < kMmaWarp) {
+    // ------------------------------------------------------------------ activation-tile stagers + weight TMA
+    const int st = tid - Cfg::kEpiThreads;  // 0..127
+    uint32_t it = 0, cnt = 0;
+    int staged_tile = -1;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int tile = item / n_chunks, chunk = item - tile * n_chunks;
+      const bool restage = tile != staged_tile;
+      staged_tile = tile;
+      if (restage) mbar_wait(a_free, (it + 1) & 1u);  // the previous tile's MMAs have finished reading the tile
+#pragma unroll 1
+      for (int kc = 0; restage && kc < Cfg::kKC; ++kc) {
+        // slot = (row r, 16-byte chunk c) = 8 consecutive K elements: two float4 loads -> 8 hi halves + 8 lo halves;
+        // four slots at a time (8 float4 in flight) to stay inside the 80-register budget of a 21-warp CTA
+        uint8_t* hi = a_smem + kc * kPackStageBytes;
+#pragma unroll 1
+        for (int j0 = 0; j0 < 8; j0 += 4) {
+          float4 va[4], vb[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = st + 128 * (j0 + j), r = idx >> 3, c = idx & 7;
+            const int gr = tile * 128 + r;
+            va[j] = vb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < n_atoms) {
+              const float4* p = reinterpret_cast<const float4*>(z + (int64_t)gr * F + kc * kPackChunk16 + c * 8);
+              va[j] = __ldg(p), vb[j] = __ldg(p + 1);
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int idx = st + 128 * (j0 + j);
+            const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+            uint4 h, l;
+            split_f16x8(va[j], vb[j], h, l);
+            *reinterpret_cast<uint4*>(hi + off) = h;
+            *reinterpret_cast<uint4*>(hi + kPackImageBytes + off) = l;
+          }
+        }
+      }
+      if (restage) {
+        fence_async_smem();
+        mbar_arrive(a_full);
+        ++it;
+      }
+      if (st == 0) {
+        const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_packed);
+        for (int oi = 0; oi < oc; ++oi) {
+          const int o = chunk * oc + oi;
+          for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
+            const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
+            mbar_wait(&empty[s], (u + 1) & 1u);
+            mbar_arrive_expect_tx(&full[s], kPackStageBytes);
+            bulk_g2s(b_smem + s * kPackStageBytes, wsrc + ((int64_t)o * Cfg::kKC + kc) * kPackStageBytes,
+                     kPackStageBytes, &full[s]);
+          }
+        }
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer
+    constexpr uint32_t idesc = umma_idesc_f16(128, F), idesc2 = umma_idesc_f16(128, 2 * F);
+    uint32_t it = 0, cnt = 0, ocount = 0;
+    int staged_tile = -1;
+    for (int item = item_lo; item < item_hi; ++item) {
+      const int tile = item / n_chunks;
+      if (tile != staged_tile) {
+        mbar_wait(a_full, it & 1u);
+        ++it;
+        staged_tile = tile;
+      }
+      tc_fence_after();
+      for (int oi = 0; oi < oc; ++oi, ++ocount) {
+        const uint32_t b = ocount & 1u;
+        mbar_wait(&tmem_empty[b], ((ocount >> 1) + 1) & 1u);
+        tc_fence_after();
+        for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
+          const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
+          mbar_wait(&full[s], u & 1u);
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes);
+            const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
+            const uint32_t d = tmem + b * 2 * F, dc = d + F;
+            // one N = 2F MMA multiplies a_hi with the adjacent [b_hi; b_lo] images (main | correction columns), one
+            // N = F MMA adds a_lo * b_hi to the correction columns; each K step is 16 halves = 32 bytes of the row
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t off = ks * 32;
+              umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+              umma_f16(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+            }
+            umma_commit(&empty[s]);
+            if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);
+          }
+          __syncwarp();
+        }
+      }
+      // last item of this atom tile: the activation tile may be overwritten once these MMAs are done
+      if ((item + 1 == item_hi || (item + 1) / n_chunks != tile) && lane == 0) umma_commit(a_free);
+      __syncwarp();
+    }
+  }
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    tc_fence_after();
+    tmem_dealloc(tmem, Cfg::kTmemCols);
+  }
+}
+
+}  // namespace
+}  // namespace cgat
+
+using namespace cgat;
+
+namespace {
+template <int kMode>
+int launch_hyper16(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
+                   const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {
+  using Cfg = Hyper16Cfg<128>;
+  if (n_atoms <= 0) return 0;
+  if (f != 128) return fail(-2, "cgat_hyper_*_f16: only F = 128 is instantiated");
+  if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_*_f16: too many atoms");
+  if (w_bias && (reinterpret_cast<uintptr_t>(w_bias) & 15)) return fail(-2, "cgat_hyper_*_f16: w_bias must be 16-byte aligned");
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_f16_kernel<128, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int n_tiles = (int)((n_atoms + 127) / 128);
+  const int oc = hyper_chunk(n_atoms, f);
+  const int n_items = n_tiles * (f / oc);
+  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  hyper_rowdot_f16_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc);
+  return check_launch(kMode == 0 ? "hyper_rowdot_f16_kernel" : "hyper_rowscale_f16_kernel");
+}
+}  // namespace
+
+// cgat_hyper_rowdot_fwd with w_packed = cgat_pack_kmajor_f16 of W[:F*F, :F]  (same arguments and result)
+extern "C" int cgat_hyper_rowdot_fwd_f16(const float* z, const float* y_in, const float* e_term, const float* e_term2,
+                                         const float* w_bias, const float* w_packed, float* y_out, int64_t n_atoms,
+                                         int32_t f, void* stream_) {
+  return launch_hyper16<0>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, f, (cudaStream_t)stream_);
+}
+
+// cgat_hyper_rowscale with w_packed = cgat_pack_kmajor_f16 of the F stacked blocks; partial: (cgat_hyper_rowscale_parts, N, F)
+extern "C" int cgat_hyper_rowscale_f16(const float* a, const float* scale, const float* w_bias, const float* w_packed,
+                                       float* partial, int64_t n_atoms, int32_t f, void* stream_) {
+  return launch_hyper16<1>(a, scale, nullptr, nullptr, w_bias, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
+}

@@ -327,14 +327,6 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
 using namespace cgat;
 
 namespace {
-// output channels per work item: smaller chunks when there are few atom tiles, so that all SMs get work
-int hyper_chunk(int64_t n_atoms, int f) {
-  const int n_tiles = (int)((n_atoms + 127) / 128);
-  int oc = 16;
-  while (oc > 4 && (int64_t)n_tiles * (f / oc) < 3 * kNumSMs) oc >>= 1;
-  return oc;
-}
-
 template <int kMode, bool kTS>
 int launch_hyper_impl(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
                       const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {

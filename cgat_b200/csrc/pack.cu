@@ -36,6 +36,34 @@ __global__ void pack_kmajor_kernel(const float* __restrict__ w, int64_t ld, int 
   }
 }
 
+
+// fp16 form (f16x3, tc_common.cuh): tiles of 128 rows x 64 halves; thread -> (row r, 16-byte chunk c = 8 halves)
+__global__ void pack_kmajor_f16_kernel(const float* __restrict__ w, int64_t ld, int rows, int k, int transpose,
+                                       float* __restrict__ out) {
+  const int kc = blockIdx.x, rt = blockIdx.y;
+  uint8_t* dst = reinterpret_cast<uint8_t*>(out) + ((int64_t)rt * gridDim.x + kc) * kPackStageBytes;
+  for (int idx = threadIdx.x; idx < kPackRows * 8; idx += blockDim.x) {
+    const int r = idx >> 3, c = idx & 7;
+    const int gr = rt * kPackRows + r, gk = kc * kPackChunk16 + c * 8;
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float x = 0.f;
+      if (gr < rows && gk + j < k) {
+        if (transpose == 0) x = w[(int64_t)gr * ld + gk + j];
+        else if (transpose == 1) x = w[(int64_t)(gk + j) * ld + gr];
+        else x = w[((int64_t)rt * kPackRows + gk + j) * ld + r];  // 2: transpose inside each 128 x 128 block
+      }
+      v[j] = x;
+    }
+    uint4 hi, lo;
+    split_f16x8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+    const uint32_t off = sw128_offset(r, c);
+    *reinterpret_cast<uint4*>(dst + off) = hi;
+    *reinterpret_cast<uint4*>(dst + kPackImageBytes + off) = lo;
+  }
+}
+
 }  // namespace
 }  // namespace cgat
 
@@ -53,4 +81,18 @@ extern "C" int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_
   dim3 grid((unsigned)ceil_div(k, tc::kPackChunk), (unsigned)ceil_div(rows, tc::kPackRows));
   pack_kmajor_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, out);
   return check_launch("pack_kmajor_kernel");
+}
+
+extern "C" int64_t cgat_packed_floats_f16(int64_t rows, int64_t k) { return tc::packed_floats_f16(rows, k); }
+
+// fp16 hi/lo form of cgat_pack_kmajor (operands of the kind::f16 kernels): same arguments, `out` holds
+// cgat_packed_floats_f16(rows, k) floats.
+extern "C" int cgat_pack_kmajor_f16(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
+                                    void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (rows <= 0 || k <= 0) return 0;
+  if (transpose == 2 && (k != tc::kPackRows || rows % tc::kPackRows)) return fail(-2, "cgat_pack_kmajor_f16: block transpose needs 128 x 128 blocks");
+  dim3 grid((unsigned)ceil_div(k, tc::kPackChunk16), (unsigned)ceil_div(rows, tc::kPackRows));
+  pack_kmajor_f16_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, out);
+  return check_launch("pack_kmajor_f16_kernel");
 }

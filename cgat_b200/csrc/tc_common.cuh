@@ -3,6 +3,7 @@
 // fp32 -> (tf32_hi, tf32_lo) split that makes three kind::tf32 passes reproduce an fp32 product
 // to ~2^-21 (the parity bar of BASELINE.json rules out a single TF32 pass).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -255,6 +256,55 @@ constexpr uint32_t kPackStageBytes = 2 * kPackImageBytes;         // hi + lo
 
 __host__ __device__ inline int64_t packed_floats(int64_t rows, int64_t k) {
   int64_t rt = (rows + kPackRows - 1) / kPackRows, kc = (k + kPackChunk - 1) / kPackChunk;
+  return rt * kc * (kPackStageBytes / 4);
+}
+
+
+// ---- kind::f16 with a SCALED fp16 hi/lo split ("f16x3") --------------------------------------------
+// x ~= hi + lo * 2^-11 with hi = rn_f16(x), lo = rn_f16((x - hi) * 2^11): 11 + 11 significand bits, the same
+// 22 bits as the tf32 hi/lo split, but the kind::f16 MMA has twice the rate of kind::tf32 and its operands are
+// half as wide (half the shared-memory operand traffic, which is what paces the M = N = 128 kernels).  The scale
+// keeps lo in fp16's normal range for |x| down to ~2^-14; the hi*lo + lo*hi products go to their own
+// accumulator (as in the tf32 kernels) and are multiplied by 2^-11 once, in the epilogue.  Only for operands that
+// are ACTIVATIONS or WEIGHTS (|x| well inside [2^-14 * 2^-11, 65504]); gradient operands stay on the tf32 kernels.
+constexpr float kF16LoScale = 2048.f;
+constexpr float kF16LoInv = 1.f / 2048.f;
+
+__host__ __device__ constexpr uint32_t umma_idesc_f16(uint32_t m, uint32_t n) {
+  return (1u << 4)               // c_format = F32; a_format = b_format = 0 (F16); both operands K-major
+         | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, fp16 operands (K = 16 per instruction), fp32 accumulate
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two fp32 -> packed (hi.x | hi.y << 16), (lo.x | lo.y << 16)
+__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+  const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
+  const __half lx = __float2half_rn((x - __half2float(hx)) * kF16LoScale);
+  const __half ly = __float2half_rn((y - __half2float(hy)) * kF16LoScale);
+  hi = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
+  lo = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
+}
+// 8 consecutive fp32 (two float4) -> one 16-byte chunk of the hi image and one of the lo image
+__device__ __forceinline__ void split_f16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
+  split_f16x2(a.x, a.y, hi.x, lo.x);
+  split_f16x2(a.z, a.w, hi.y, lo.y);
+  split_f16x2(b.x, b.y, hi.z, lo.z);
+  split_f16x2(b.z, b.w, hi.w, lo.w);
+}
+
+// Packed K-major fp16 operand: tiles of kPackRows rows x kPackChunk16 halves (128-byte rows, SWIZZLE_128B), stored
+// as [row_tile][k_chunk][hi|lo] 16 KB images like the tf32 form; one 32 KB stage now covers 64 contraction steps.
+constexpr int kPackChunk16 = 64;
+__host__ __device__ inline int64_t packed_floats_f16(int64_t rows, int64_t k) {
+  int64_t rt = (rows + kPackRows - 1) / kPackRows, kc = (k + kPackChunk16 - 1) / kPackChunk16;
   return rt * kc * (kPackStageBytes / 4);
 }
 

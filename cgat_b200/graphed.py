@@ -1,0 +1,159 @@
+"""Whole-step CUDA graphs for CGAtNet: one captured graph per shape bucket, replayed from static buffers.
+
+A default-config train step is ~230 launches of this library's kernels plus ~700 small library kernels; enqueueing
+them from Python takes about as long as the GPU needs to run them (profiles/: host enqueue 27 ms vs 31 ms of GPU
+time at 500 crystals).  The reference has the same structure through PyG / Lightning and no answer to it.  Here a
+step is captured ONCE per bucket signature (cgat_b200/batching.py pads ragged batches to bucket boundaries with a
+dummy crystal) — forward, loss, backward, gradient all-reduce and AdamW in one graph — and every later step of that
+bucket is three things: copy the batch into the graph's static input buffers, `cudaGraphLaunch`, read the loss.
+
+Rules the capture relies on (all checked by tests/test_gpu_model.py::test_graphed_step_matches_eager):
+  * nothing in CGAtNet.forward / backward syncs with the host or has data-dependent shapes (GraphBatch.num_graphs is
+    a host int; all plans are built by kernels);
+  * the C ABI never allocates, copies from host memory or synchronises (include/cgat_b200.h), so every entry point is
+    capturable; pointer arrays are passed by value in kernel parameters;
+  * packed weight images are rebuilt INSIDE the graph (ops.invalidate_packed before capture), because replays
+    update the weights without Python noticing;
+  * the optimizer is created with capturable=True and has run once eagerly (its state exists) before any capture;
+  * gradients are graph-private (p.grad = None before capture), so no accumulate kernels exist and zero_grad is free.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib, batching, ops
+
+
+class _Slot:
+    """One captured graph + its static inputs / outputs."""
+    __slots__ = ("graph", "inputs", "target", "out", "loss", "launches")
+
+
+def _static_like(sb, dev):
+    """Device buffers with the shapes of a (padded) batch; the graph reads its inputs from these."""
+    return sb.to(dev)
+
+
+def _copy_batch(dst, src):
+    """src (pinned host or device) -> the static buffers of a slot; non_blocking so that the copies queue behind
+    each other on the current stream and the host runs ahead."""
+    for d, s in zip(dst.graph.tensors(), src.graph.tensors()):
+        d.copy_(s, non_blocking=True)
+    for d, s in zip(dst.roost, src.roost):
+        d.copy_(s, non_blocking=True)
+
+
+class GraphedTrainStep:
+    """step(padded_batch, target) -> loss (0-dim device tensor, valid until the next step of the same bucket).
+
+    `loss_fn(pred_real, target_real)` sees the rows of the real crystals only.  `sync` is a distributed.GradSync (its
+    all-reduce is captured with the rest).  The first `eager_steps` calls run eagerly (lazy library initialisation,
+    optimizer state), later calls capture on the first use of a bucket and replay afterwards."""
+
+    def __init__(self, model, optimizer, loss_fn, sync=None, eager_steps=1):
+        for grp in optimizer.param_groups:
+            if not grp.get("capturable", False):
+                raise ValueError("GraphedTrainStep needs an optimizer created with capturable=True")
+        self.model, self.opt, self.loss_fn, self.sync = model, optimizer, loss_fn, sync
+        self.eager_left = max(1, int(eager_steps))
+        self.slots = {}
+        self.pool = None
+        self.replayed_launches = 0      # kernels of this library executed through graph replays
+        self.captures = 0
+
+    # -- the step itself, as Python: used eagerly and under capture
+    def _body(self, sb, target):
+        out = self.model(sb.graph, sb.roost)
+        n_real = sb.graph.num_graphs - 1
+        loss = self.loss_fn(out[:n_real, :1], target[:n_real])
+        loss.backward()
+        if self.sync is not None:
+            self.sync.all_reduce()
+        self.opt.step()
+        return out, loss
+
+    def _drop_grads(self):
+        if self.sync is not None:
+            self.sync.zero_grad()
+        for p in self.model.parameters():
+            p.grad = None
+
+    def step(self, sb, target):
+        """sb: batching.pad_batch output (pinned host or device tensors); target: (C+1, 1) normalised targets."""
+        dev = next(self.model.parameters()).device
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            self._drop_grads()
+            out, loss = self._body(sb.to(dev, non_blocking=True), target.to(dev, non_blocking=True))
+            return loss.detach()
+        sig = batching.signature(sb)
+        slot = self.slots.get(sig)
+        if slot is None:
+            slot = self._capture(sig, sb, target, dev)
+        _copy_batch(slot.inputs, sb)
+        slot.target.copy_(target, non_blocking=True)
+        slot.graph.replay()
+        self.replayed_launches += slot.launches
+        ops.invalidate_packed()          # the replay changed the weights behind Python's back
+        return slot.loss
+
+    def _capture(self, sig, sb, target, dev):
+        slot = _Slot()
+        slot.inputs = _static_like(sb, dev)
+        slot.target = target.to(dev).clone()
+        torch.cuda.synchronize()
+        self._drop_grads()
+        ops.invalidate_packed()          # the graph must contain its own pack launches
+        slot.graph = torch.cuda.CUDAGraph()
+        before = _lib.launch_count()
+        with torch.cuda.graph(slot.graph, pool=self.pool):
+            out, loss = self._body(slot.inputs, slot.target)
+            slot.out, slot.loss = out.detach(), loss.detach()
+        slot.launches = _lib.launch_count() - before
+        if self.pool is None:
+            self.pool = slot.graph.pool()
+        self.slots[sig] = slot
+        self.captures += 1
+        return slot
+
+
+class GraphedForward:
+    """forward(padded_batch) -> predictions of the real crystals (C, out) as a view of the graph's static output
+    (valid until the next call on the same bucket).  Inference: weights are static, packed images are built by the
+    eager warm-up call and reused by every graph."""
+
+    def __init__(self, model, eager_calls=1):
+        self.model = model
+        self.eager_left = max(1, int(eager_calls))
+        self.slots = {}
+        self.pool = None
+        self.replayed_launches = 0
+        self.captures = 0
+
+    @torch.no_grad()
+    def __call__(self, sb):
+        dev = next(self.model.parameters()).device
+        n_real = sb.graph.num_graphs - 1
+        if self.eager_left > 0:
+            self.eager_left -= 1
+            d = sb.to(dev, non_blocking=True)
+            return self.model(d.graph, d.roost)[:n_real]
+        sig = batching.signature(sb)
+        slot = self.slots.get(sig)
+        if slot is None:
+            slot = _Slot()
+            slot.inputs = _static_like(sb, dev)
+            torch.cuda.synchronize()
+            slot.graph = torch.cuda.CUDAGraph()
+            before = _lib.launch_count()
+            with torch.cuda.graph(slot.graph, pool=self.pool):
+                slot.out = self.model(slot.inputs.graph, slot.inputs.roost)
+            slot.launches = _lib.launch_count() - before
+            if self.pool is None:
+                self.pool = slot.graph.pool()
+            self.slots[sig] = slot
+            self.captures += 1
+        _copy_batch(slot.inputs, sb)
+        slot.graph.replay()
+        self.replayed_launches += slot.launches
+        return slot.out[:n_real]

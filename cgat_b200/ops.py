@@ -80,6 +80,8 @@ LEAKY_SLOPE = 0.01
 _FUSED = os.environ.get("CGAT_B200_FUSED", "1") != "0"
 _TN_WGRAD = os.environ.get("CGAT_B200_TN", "1") != "0"   # weight gradients on cgat_gemm3x_tn vs library mm
 _TRUNK = os.environ.get("CGAT_B200_TRUNK", "1") != "0"   # hypernetwork trunks: fused chain kernel vs library GEMMs
+# activation x weight tensor-core kernels on kind::f16 with scaled fp16 hi/lo operands (1) or kind::tf32 hi/lo (0)
+_F16X3 = os.environ.get("CGAT_B200_F16X3", "1") != "0"
 
 
 def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
@@ -184,25 +186,37 @@ def gemm3x_tn(a, b, n_split=None):
     return part[0] if n_split == 1 else part.sum(dim=0)
 
 
-def packed_kmajor(w, rows=None, transpose=False):
+# Packed operand caches are keyed on the weight's autograd version.  A CUDA-graph replay updates weights without
+# Python seeing it, so cgat_b200/graphed.py bumps this epoch (a) before every capture of a training graph, which
+# makes the capture contain its own pack launches, and (b) after every replay, so eager code repacks too.
+_pack_epoch = 0
+
+
+def invalidate_packed():
+    global _pack_epoch
+    _pack_epoch += 1
+
+
+def packed_kmajor(w, rows=None, transpose=False, f16=False):
     """Pre-split / pre-swizzled copy of w[:rows] (2-D view of a contiguous weight) for the fused
-    kernels.  Cached ON the tensor object and keyed by its autograd version counter, so an in-place
-    optimizer update (which bumps `_version`) triggers a repack and a freed tensor cannot leave a
-    stale entry behind."""
+    kernels (tf32 hi/lo images, or scaled fp16 hi/lo images with f16=True).  Cached ON the tensor object and
+    keyed by its autograd version counter, so an in-place optimizer update (which bumps `_version`) triggers a
+    repack and a freed tensor cannot leave a stale entry behind."""
     w2 = w.detach().view(w.shape[0], -1)
     rows = w2.shape[0] if rows is None else rows
     cache = w.__dict__.setdefault("_cgat_packed", {})
-    key = (rows, int(transpose))
+    key = (rows, int(transpose), bool(f16))
     hit = cache.get(key)
-    if hit is not None and hit[0] == w._version and hit[2] == w.data_ptr():
+    if hit is not None and hit[0] == (w._version, _pack_epoch) and hit[2] == w.data_ptr():
         return hit[1]
     lib = _lib.load()
     n_rows, k = (w2.shape[1], rows) if int(transpose) == 1 else (rows, w2.shape[1])
-    buf = hit[1] if hit is not None else torch.empty(int(lib.cgat_packed_floats(n_rows, k)), dtype=torch.float32,
-                                                     device=w.device)
-    _lib.call("cgat_pack_kmajor", _lib.ptr(w2), w2.stride(0), n_rows, k, int(transpose), _lib.ptr(buf),
-              _lib.stream(), work=dict(key="pack_kmajor", bound="hbm", bytes=12.0 * n_rows * k))
-    cache[key] = (w._version, buf, w.data_ptr())
+    size = lib.cgat_packed_floats_f16(n_rows, k) if f16 else lib.cgat_packed_floats(n_rows, k)
+    buf = hit[1] if hit is not None else torch.empty(int(size), dtype=torch.float32, device=w.device)
+    _lib.call("cgat_pack_kmajor_f16" if f16 else "cgat_pack_kmajor", _lib.ptr(w2), w2.stride(0), n_rows, k,
+              int(transpose), _lib.ptr(buf), _lib.stream(),
+              work=dict(key="pack_kmajor", bound="hbm", bytes=(8.0 if f16 else 12.0) * n_rows * k))
+    cache[key] = ((w._version, _pack_epoch), buf, w.data_ptr())
     return buf
 
 
@@ -213,8 +227,9 @@ class _HyperLinear(torch.autograd.Function):
     bias tail, W[F*F:] z + b[F*F:], when the fused trunk kernel has already produced it."""
 
     @staticmethod
-    def forward(ctx, z, weight, bias, y, e, w_packed, w_packed_bt):
+    def forward(ctx, z, weight, bias, y, e, w_packed, w_packed_bt, f16):
         z, y = _f32c(z), _f32c(y)
+        ctx.f16 = f16
         n, f = y.shape
         ff = f * f
         bias = bias.contiguous()
@@ -224,10 +239,12 @@ class _HyperLinear(torch.autograd.Function):
             e = gemm3x(z, weight[ff:], bias[ff:])
         out = torch.empty_like(y)
         # the bias of the predicted weights, b[:F*F], is added inside the kernel's epilogue
-        _lib.call("cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y), _lib.ptr(_f32c(e)), None, _lib.ptr(bias),
+        _lib.call("cgat_hyper_rowdot_fwd_f16" if f16 else "cgat_hyper_rowdot_fwd", _lib.ptr(z), _lib.ptr(y),
+                  _lib.ptr(_f32c(e)), None, _lib.ptr(bias),
                   _lib.ptr(w_packed), _lib.ptr(out), n, f, _lib.stream(),
                   work=dict(key="hyper_rowdot_fwd", bound="tensor", flops=2.0 * n * f * ff,
-                            note="3xTF32: 3 tensor passes per algorithmic flop"))
+                            note="f16x3: 3 kind::f16 passes per algorithmic flop" if f16 else
+                            "3xTF32: 3 tensor passes per algorithmic flop"))
         ctx.save_for_backward(z, weight, bias, y, w_packed, w_packed_bt)
         return out
 
@@ -238,17 +255,19 @@ class _HyperLinear(torch.autograd.Function):
         ff = f * f
         g = _f32c(g)
         parts = int(_lib.load().cgat_hyper_rowscale_parts(n, f))
+        rowscale = "cgat_hyper_rowscale_f16" if ctx.f16 else "cgat_hyper_rowscale"
         work = dict(key="hyper_rowscale", bound="tensor", flops=2.0 * n * f * ff,
-                    note="3xTF32: 3 tensor passes per algorithmic flop")
+                    note="f16x3: 3 kind::f16 passes per algorithmic flop" if ctx.f16 else
+                    "3xTF32: 3 tensor passes per algorithmic flop")
         # dL/dy[n,i] = sum_o g[n,o] (W z[n] + b)[o*F+i]: recomputed tile by tile on the tensor cores
         bias = bias.contiguous()
         buf = torch.empty((parts, n, f), dtype=torch.float32, device=y.device)
-        _lib.call("cgat_hyper_rowscale", _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed), _lib.ptr(buf),
+        _lib.call(rowscale, _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed), _lib.ptr(buf),
                   n, f, _lib.stream(), work=work)
         g_y = buf.sum(dim=0)
         # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ the bias-tail rows unless they went through `e`)
         buf2 = torch.empty_like(buf)
-        _lib.call("cgat_hyper_rowscale", _lib.ptr(y), _lib.ptr(g), None, _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
+        _lib.call(rowscale, _lib.ptr(y), _lib.ptr(g), None, _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
                   _lib.stream(), work=work)
         g_z = buf2.sum(dim=0)
         if not ctx.has_e:
@@ -269,7 +288,7 @@ class _HyperLinear(torch.autograd.Function):
         gyz = gemm3x_tn(g, yz)                             # (F, 2F), split over atoms to fill the SMs
         g_w[ff:] = gyz[:, f:]
         g_b = torch.cat([gyz[:, :f].reshape(ff), g.sum(dim=0)])
-        return g_z, g_w, g_b, g_y, (g if ctx.has_e else None), None, None
+        return g_z, g_w, g_b, g_y, (g if ctx.has_e else None), None, None, None
 
 
 def hyper_linear(z, weight, bias, y, out_ch, e=None):
@@ -278,8 +297,9 @@ def hyper_linear(z, weight, bias, y, out_ch, e=None):
     `e`: weight[out*in:] z + bias[out*in:] if hyper_trunks has already computed it (fused path only)."""
     in_ch = y.shape[1]
     if _FUSED and z.is_cuda and in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
-        return _HyperLinear.apply(z, weight, bias, y, e, packed_kmajor(weight, in_ch * out_ch),
-                                  packed_kmajor(weight, in_ch * out_ch, 2) if torch.is_grad_enabled() else None)
+        return _HyperLinear.apply(z, weight, bias, y, e, packed_kmajor(weight, in_ch * out_ch, f16=_F16X3),
+                                  packed_kmajor(weight, in_ch * out_ch, 2, f16=_F16X3) if torch.is_grad_enabled()
+                                  else None, _F16X3)
     p = torch.addmm(bias, z, weight.t())                            # (N, out*in + out)
     w = p[:, : in_ch * out_ch].view(-1, out_ch, in_ch)
     b = p[:, in_ch * out_ch:]
@@ -315,7 +335,7 @@ def gemm3x_tn_batched(a_list, b_list, colsum=True):
 def _trunk_packed(weights, transpose):
     """Packed chain operands of a list of F x F weights (cgat_hyper_trunk_pack), cached on the first tensor and
     keyed by the autograd versions / addresses of all of them (an optimizer step triggers a repack)."""
-    key = tuple((w._version, w.data_ptr()) for w in weights)
+    key = (_pack_epoch,) + tuple((w._version, w.data_ptr()) for w in weights)
     cache = weights[0].__dict__.setdefault("_cgat_trunk_packed", {})
     hit = cache.get(transpose)
     if hit is not None and hit[0] == key:
@@ -416,12 +436,12 @@ def _w2_transposed_packed(w2, heads):
     """Packed W2^T per head, (H*Hd, F): row h*Hd+k, col c = W2[h*F+c, k] — the A operand of the dgrad MMAs."""
     cache = w2.__dict__.setdefault("_cgat_packed", {})
     hit = cache.get("w2t")
-    if hit is not None and hit[0] == w2._version and hit[2] == w2.data_ptr():
+    if hit is not None and hit[0] == (w2._version, _pack_epoch) and hit[2] == w2.data_ptr():
         return hit[1]
     hf, hd = w2.shape[0], w2.shape[1]
     wt = w2.detach().view(heads, hf // heads, hd).transpose(1, 2).reshape(heads * hd, hf // heads).contiguous()
     buf = packed_kmajor(wt).clone() if hit is None else hit[1].copy_(packed_kmajor(wt))
-    cache["w2t"] = (w2._version, buf, w2.data_ptr())
+    cache["w2t"] = ((w2._version, _pack_epoch), buf, w2.data_ptr())
     return buf
 
 
@@ -430,7 +450,7 @@ def _first_layer_operands(w1a, w1m, b1a, b1m, f, fe):
     [W1A_i; W1M_i; W1A_j; W1M_j] (+ its packed image), per-rank block (2*HHd, Fe) = [W1A_e; W1M_e] and the
     concatenated bias.  Cached on the weight and keyed by the autograd versions, so screening inference builds
     them once and training once per optimizer step."""
-    key = tuple((t._version, t.data_ptr()) for t in (w1a, w1m, b1a, b1m))
+    key = (_pack_epoch,) + tuple((t._version, t.data_ptr()) for t in (w1a, w1m, b1a, b1m))
     cache = w1a.__dict__.setdefault("_cgat_first_layer", {})
     if cache.get("key") == key:
         return cache["val"]

@@ -109,6 +109,12 @@ int cgat_gemm3x_tn_batched(const float* const* A, const float* const* B, int32_t
 int64_t cgat_packed_floats(int64_t rows, int64_t k);
 int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
                      void* stream);
+/* fp16 hi/lo form ("f16x3": x ~= hi + lo * 2^-11, both fp16; the same 22 significand bits as the tf32 pair) for the
+ * kind::f16 kernels below, whose operands are activations and weights: tiles of 128 rows x 64 halves, otherwise the
+ * same layout, arguments and repack rule.  `out` holds cgat_packed_floats_f16(rows,k) floats.      */
+int64_t cgat_packed_floats_f16(int64_t rows, int64_t k);
+int cgat_pack_kmajor_f16(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
+                         void* stream);
 
 /* ---- fused hypernetwork linear layer ----------------------------------
  * y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k] + w_bias[o*F+i]) * y_in[n,i] + e_term[n,o]
@@ -164,6 +170,13 @@ int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, co
 int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f);
 int cgat_hyper_rowscale(const float* a, const float* scale, const float* w_bias, const float* w_packed,
                         float* partial, int64_t n_atoms, int32_t f, void* stream);
+/* The same two products on kind::f16 passes (twice the tensor rate, half the shared-memory operand traffic):
+ * identical arguments and results, w_packed = cgat_pack_kmajor_f16(...) (hyper_f16.cu).           */
+int cgat_hyper_rowdot_fwd_f16(const float* z, const float* y_in, const float* e_term, const float* e_term2,
+                              const float* w_bias, const float* w_packed, float* y_out, int64_t n_atoms, int32_t f,
+                              void* stream);
+int cgat_hyper_rowscale_f16(const float* a, const float* scale, const float* w_bias, const float* w_packed,
+                            float* partial, int64_t n_atoms, int32_t f, void* stream);
 
 /* Weight gradient of the hyper-linear layer: dL/dW[o*F+i, k] = sum_n g[n,o] y[n,i] z[n,k], contracted over
  * atoms with MN-major operands; the scaled rows g[n,o]*y[n,:] are formed while staging (the reference's

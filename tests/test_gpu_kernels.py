@@ -106,10 +106,13 @@ def test_library_loaded_and_counting():
     assert _lib.launch_count() > before
 
 
+@pytest.mark.parametrize("f16", [True, False], ids=["f16x3", "tf32x3"])
 @pytest.mark.parametrize("n", [1, 119, 128, 700, 5559])
-def test_hyper_linear_fused_fwd_bwd(n):
-    """cgat_hyper_rowdot_fwd (+ e-term GEMM) against the reference arithmetic in fp64
-    (HyperLinear.forward + BatchLinear.forward, reference CGAT/Hypernetworksmp.py:243-254, 205-209)."""
+def test_hyper_linear_fused_fwd_bwd(n, f16, monkeypatch):
+    """cgat_hyper_rowdot_fwd[_f16] / cgat_hyper_rowscale[_f16] (+ e-term GEMM) against the reference arithmetic in
+    fp64 (HyperLinear.forward + BatchLinear.forward, reference CGAT/Hypernetworksmp.py:243-254, 205-209), with the
+    MMA operands as scaled fp16 hi/lo pairs and as tf32 hi/lo pairs: same tolerance for both."""
+    monkeypatch.setattr(ops, "_F16X3", f16)
     f = 128
     g = torch.Generator().manual_seed(n)
     z = torch.tanh(torch.randn(n, f, generator=g))

@@ -106,3 +106,77 @@ def test_edge_order_invariance():
         a = model(g.to(DEV), tuple(t.to(DEV) for t in sb.roost))
         b = model(g2.to(DEV), tuple(t.to(DEV) for t in sb.roost))
     assert_close(a, b, "edge order", atol=2e-5, rtol=1e-4)
+
+
+def test_padded_batch_matches_unpadded():
+    """batching.pad_batch on the device path: predictions of the real crystals are unchanged by the dummy crystal."""
+    from cgat_b200 import batching
+    model, sb = _gpu_model("default_k12")
+    pb = batching.pad_batch(sb)
+    C = sb.num_crystals
+    with torch.no_grad():
+        ref = model(sb.graph.to(DEV), tuple(t.to(DEV) for t in sb.roost))
+        pad = model(pb.graph.to(DEV), tuple(t.to(DEV) for t in pb.roost))
+    assert pad.shape[0] == C + 1 and torch.isfinite(pad).all()
+    assert_close(pad[:C], ref, "padded forward", atol=2e-5, rtol=1e-4)
+
+
+def _train_setup(seed=0):
+    mkw = CASES["default_k12"][0]
+    model = weights.load_seeded(cgat_b200.CGAtNet(200, **mkw), seed).to(DEV)
+    opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-6, fused=True, capturable=True)
+    return model, opt
+
+
+def test_graphed_step_matches_eager():
+    """graphed.GraphedTrainStep (one CUDA graph per shape bucket: forward, loss, backward, AdamW) follows the eager
+    loop step for step: same losses and same weights after steps that cross two buckets and revisit the first."""
+    from cgat_b200 import batching, graphed
+    from cgat_b200 import distributed as cdist
+    batches = [batching.pad_batch(synthetic.make_batch(40, 12, seed=s)) for s in (1, 2, 1, 2, 1)]
+    batches += [batching.pad_batch(synthetic.make_batch(90, 12, seed=3)),
+                batching.pad_batch(synthetic.make_batch(40, 12, seed=2))]      # back to the first bucket's graph
+    assert len({batching.signature(b) for b in batches}) >= 2
+    tg = []
+    for b in batches:
+        y = b.graph.y
+        tg.append((y / y.abs().max()).view(-1, 1).to(DEV))
+    crit = torch.nn.L1Loss()
+
+    model_e, opt_e = _train_setup()
+    sync_e = cdist.GradSync(model_e, 1)
+    eager_losses = []
+    for b, t in zip(batches, tg):
+        d = b.to(DEV)
+        n_real = d.graph.num_graphs - 1
+        loss = crit(model_e(d.graph, d.roost)[:n_real, :1], t[:n_real])
+        loss.backward()
+        opt_e.step()
+        sync_e.zero_grad()
+        eager_losses.append(float(loss))
+
+    model_g, opt_g = _train_setup()
+    runner = graphed.GraphedTrainStep(model_g, opt_g, crit, cdist.GradSync(model_g, 1))
+    before = _lib.launch_count()
+    graph_losses = [float(runner.step(b.pin_memory(), t)) for b, t in zip(batches, tg)]
+    assert runner.captures >= 2 and runner.replayed_launches > 0 and _lib.launch_count() > before
+    for i, (a, b) in enumerate(zip(graph_losses, eager_losses)):
+        assert abs(a - b) <= 1e-6 + 1e-5 * abs(b), f"step {i}: graphed loss {a} vs eager {b}"
+    pe, pg = dict(model_e.named_parameters()), dict(model_g.named_parameters())
+    for k in ("embedding.weight", "graphs.0.Node.MH_M.fc_in.weight", "graphs.4.Node.MH_A.fc_out.weight",
+              "graphs.2.Node.Pooling_NN.Hyper.layers.1.hyper_linear.hypo_params.net.4.weight", "output_nn.fc_out.weight"):
+        assert_close(pg[k].detach(), pe[k].detach(), f"weights after 7 steps: {k}", atol=1e-6, rtol=1e-5)
+
+
+def test_graphed_forward_matches_eager():
+    from cgat_b200 import batching, graphed
+    model, _ = _gpu_model("default_k12")
+    runner = graphed.GraphedForward(model)
+    for s in (5, 6, 5, 7):
+        sb = synthetic.make_batch(64, 12, seed=s)
+        pb = batching.pad_batch(sb)
+        out = runner(pb.pin_memory()).clone()
+        with torch.no_grad():
+            ref = model(sb.graph.to(DEV), tuple(t.to(DEV) for t in sb.roost))
+        assert_close(out, ref, f"graphed forward seed {s}", atol=2e-5, rtol=1e-4)
+    assert runner.captures >= 1 and runner.replayed_launches > 0

@@ -84,3 +84,31 @@ def test_shard_bounds_balance_edges():
     assert all(b[1] == c[0] for b, c in zip(bounds, bounds[1:]))
     loads = [int(sb.n_atoms[lo:hi].sum()) for lo, hi in bounds]
     assert max(loads) - min(loads) <= 2 * 20  # within two crystals of perfect balance
+
+
+def test_padding_is_invisible(emulated_kernels):
+    """batching.pad_batch (bucketed shapes for CUDA-graph replay) adds one dummy crystal: the real crystals'
+    predictions and every parameter gradient of a loss over the real crystals are unchanged."""
+    from cgat_b200 import batching
+    model, sb = _model("mixed_flags")
+    C = sb.num_crystals
+    pb = batching.pad_batch(sb, buckets=(64, 16, 128))
+    n, nc, mc = pb.graph.x.shape[0], pb.roost[1].shape[0], pb.roost[2].shape[0]
+    assert n % 64 == 0 and nc % 16 == 0 and mc % 128 == 0 and n > sb.graph.x.shape[0] and nc > sb.roost[1].shape[0]
+    assert pb.graph.num_graphs == C + 1 and pb.graph.edge_index.shape[1] == n * (sb.graph.edge_index.shape[1] // sb.graph.x.shape[0])
+    assert bool((pb.roost[2][1:] >= pb.roost[2][:-1]).all()) and int(pb.roost[3].max()) < nc
+    assert batching.signature(pb) == (n, pb.graph.edge_index.shape[1], C + 1, nc, mc)
+
+    def grads(batch, rows):
+        model.zero_grad(set_to_none=True)
+        out = model(batch.graph, batch.roost)
+        training_scalar(out[:rows], sb.graph.y).backward()
+        return out[:rows].detach(), {k: p.grad.clone() for k, p in model.named_parameters() if p.grad is not None}
+
+    out_ref, g_ref = grads(sb, C)
+    out_pad, g_pad = grads(pb, C)
+    assert torch.isfinite(model(pb.graph, pb.roost)).all()
+    assert_close(out_pad, out_ref, "padded forward", atol=1e-6, rtol=1e-6)
+    assert g_ref.keys() == g_pad.keys()
+    for k in g_ref:
+        assert_close(g_pad[k], g_ref[k], f"padded grad {k}", atol=1e-6, rtol=1e-5)
