@@ -209,13 +209,14 @@ def run_ours(args):
     d2h = 4 if train else wl["crystals"] * 4
 
     roof = cpu = None
-    if rank == 0:
+    if rank == 0 or (train and world > 1):
+        # the profiled steps contain the gradient all-reduce, so on several ranks every rank runs them (rank 0 reports)
         if runner is not None and train:
             for p in model.parameters():
                 p.grad = None                                 # the graphs own their gradient buffers
         roof = roofline(model, dev_pool[0], targets[0], train, step, args)
-        if not args.no_cpu_baseline:
-            cpu = cpu_baseline(wl, net_kw, train)
+    if rank == 0 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(wl, net_kw, train)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -226,7 +227,8 @@ def run_ours(args):
     if runner is not None:
         graph_cfg = {"captures": runner.captures, "buckets_atoms_elems_pairs": list(batching.DEFAULT_BUCKETS),
                      "padded_atoms": int(sum(sb.graph.x.shape[0] for sb in pool) / len(pool)),
-                     "note": "one whole-step graph per shape bucket (forward, loss, backward, all-reduce, AdamW); "
+                     "note": "one whole-step graph per shape bucket (forward, loss, backward, AdamW; on >1 rank the NCCL "
+                             "all-reduce and AdamW follow the graph eagerly); "
                              "batches padded with one dummy crystal; throughput counts real crystals only"}
     line = {
         "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),

@@ -36,6 +36,10 @@ SIGNATURES = {
     "cgat_pack_kmajor": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
     "cgat_packed_floats_f16": (_I64, [_I64, _I64]),
     "cgat_pack_kmajor_f16": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _P, _P]),
+    "cgat_pack_kmajor_f16s": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _F32, _F32, _P, _P]),
+    "cgat_edge_attn_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
+                                              _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_bwd_prep_f16": (ctypes.c_int, [_P] * 17 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
     "cgat_hyper_rowdot_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowscale_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),

@@ -107,7 +107,17 @@ __device__ __forceinline__ float fast_rcp(float x) {
 // kMode 0: forward (segmented online softmax, writes out / max / den)
 // kMode 1: backward-prep: recompute a, v and emit  d_msg = alpha * g,  d_gate = alpha * (v - out) * g  per edge
 //          (alpha from the saved per-segment max / den) plus the sign masks of the hidden pre-activations.
-template <int kMode>
+// kF16: both MMA operands as fp16 hi/lo pairs on kind::f16 (twice the rate of kind::tf32 and — what matters here — half
+// the bytes of the W2 stream: ncu r01c shows this kernel moving 27 KB per edge from L2, 20 KB of which is every CTA
+// re-reading W2 for each 128-edge tile).  The three products share ONE accumulator (TMEM has no room for a separate
+// correction accumulator next to the gate / message double buffer), so the lo parts cannot carry their own 2^11
+// scale; instead the operands are PRE-scaled by powers of two (hidden x 2^4, W2 x 2^6: cgat_pack_kmajor_f16s) which
+// lifts the lo parts of typical values into fp16's normal range and puts the absolute error floor of small values
+// (2^-25 / scale) below the fp32 rounding error of the typical ones; the accumulator is multiplied by 2^-10 in the
+// epilogue.  Valid while |hidden| < 4094 (fp16 overflow), far beyond what a non-diverged network produces.
+constexpr float kHidScale = 16.f, kW2Scale = 64.f, kF16AccInv = 1.f / (16.f * 64.f);
+
+template <int kMode, bool kF16>
 __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -125,7 +135,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = g.heads, hd = g.hd, hhd = H * hd;
-  const int kcn = (hd + 31) / 32;
+  constexpr int kChunk = kF16 ? kPackChunk16 : kPackChunk;  // hidden units per pipeline stage
+  const int kcn = (hd + kChunk - 1) / kChunk;
+  const float acc_scale = kF16 ? kF16AccInv : 1.f;
 
   if (tid == 0) {
     for (int s = 0; s < kEStages; ++s) {
@@ -215,8 +227,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                 if (g.smax != nullptr) g.smax[po] = m, g.sden[po] = den;
                 m = -INFINITY, den = 0.f, acc = 0.f;
               }
-              const float a = ((valid >> j) & 1u) ? av[j] + ba : -INFINITY;  // padding columns contribute exp(-inf) = 0
-              const float v = vv[j] + bm;
+              const float a = ((valid >> j) & 1u) ? fmaf(av[j], acc_scale, ba) : -INFINITY;  // padding: exp(-inf) = 0
+              const float v = fmaf(vv[j], acc_scale, bm);
               if (a - m > 16.f) {  // first edge of a segment (m = -inf), or a rare much larger gate
                 const float r = fast_exp(m - a);
                 den *= r, acc *= r, m = a;
@@ -258,7 +270,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             const uint32_t valid = ((uint32_t)mt[4 * kET + 4 + (cc >> 2)]) >> ((cc & 3) * 8);
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-              const float a = av[j] + ba, v = vv[j] + bm;
+              const float a = fmaf(av[j], acc_scale, ba), v = fmaf(vv[j], acc_scale, bm);
               const float alpha = fast_exp(a - sm[j]) * fast_rcp(sd[j] + g.eps);
               const float ag = alpha * sg_[j];
               if ((valid >> j) & 1u) {
@@ -315,47 +327,109 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               mbar_expect_tx(&full[s], kPackStageBytes);
               bulk_g2s(st, w2[net] + ((int64_t)h * kcn + kc) * kPackStageBytes, kPackStageBytes, &full[s]);
             }
-            float4 pd[4], ps[4], te[4];
-            const int col0 = h * hd + kc * 32;
+            if constexpr (kF16) {
+              // slot = (edge row r, 16-byte chunk c) = 8 consecutive hidden units: two float4 from each of the three
+              // gathered rows; two slots at a time (12 float4 in flight, like the tf32 path)
+              uint8_t* bh = st + kPackStageBytes;
+              const int col0 = h * hd + kc * kPackChunk16;
+#pragma unroll 1
+              for (int j0 = 0; j0 < 4; j0 += 2) {
+                float4 pd[2][2], ps[2][2], te[2][2];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int cch = (pl + kEGroup * j) & 7;
-              const int col = col0 + cch * 4;
-              const bool ok = rd[j] >= 0 && (kc * 32 + cch * 4) < hd;
-              pd[j] = ps[j] = te[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (ok) {
-                pd[j] = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)rd[j] * ldp + net * hhd + col));
-                ps[j] = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)rs[j] * ldp + 2 * hhd + net * hhd + col));
-                te[j] = __ldg(reinterpret_cast<const float4*>(g.T + (int64_t)rr[j] * ldt + net * hhd + col));
-              }
-            }
-            uint8_t* bh = st + kPackStageBytes;
+                for (int jj = 0; jj < 2; ++jj) {
+                  const int j = j0 + jj;
+                  const int cch = (pl + kEGroup * j) & 7;
+                  const int col = col0 + cch * 8;
+                  const bool ok = rd[j] >= 0 && (kc * kPackChunk16 + cch * 8) < hd;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int idx = pl + kEGroup * j;
-              float4 x;
-              x.x = pd[j].x + ps[j].x + te[j].x;
-              x.y = pd[j].y + ps[j].y + te[j].y;
-              x.z = pd[j].z + ps[j].z + te[j].z;
-              x.w = pd[j].w + ps[j].w + te[j].w;
-              if (kMode == 1) {
-                // which side of the LeakyReLU each hidden pre-activation is on: byte j' = component j' of the
-                // float4, bit c = 16-byte chunk c of the 128-byte row  ->  hidden unit c*4 + j' of this K chunk
-                const uint32_t b0 = __ballot_sync(0xffffffffu, x.x > 0.f), b1 = __ballot_sync(0xffffffffu, x.y > 0.f);
-                const uint32_t b2 = __ballot_sync(0xffffffffu, x.z > 0.f), b3 = __ballot_sync(0xffffffffu, x.w > 0.f);
-                const int sh = lane & 24;  // the 8 lanes that share an edge row
-                const uint32_t word = ((b0 >> sh) & 0xFFu) | (((b1 >> sh) & 0xFFu) << 8) | (((b2 >> sh) & 0xFFu) << 16) |
-                                      (((b3 >> sh) & 0xFFu) << 24);
-                const int r = idx >> 3;
-                if ((lane & 7) == 0 && r < nv)
-                  g.signs[((int64_t)(net * H + h) * kcn + kc) * g.n_edges + e0 + r] = word;
+                  for (int q = 0; q < 2; ++q) pd[jj][q] = ps[jj][q] = te[jj][q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                  if (ok) {
+                    const float4* a = reinterpret_cast<const float4*>(g.P + (int64_t)rd[j] * ldp + net * hhd + col);
+                    const float4* b = reinterpret_cast<const float4*>(g.P + (int64_t)rs[j] * ldp + 2 * hhd + net * hhd + col);
+                    const float4* c = reinterpret_cast<const float4*>(g.T + (int64_t)rr[j] * ldt + net * hhd + col);
+                    pd[jj][0] = __ldg(a), pd[jj][1] = __ldg(a + 1);
+                    ps[jj][0] = __ldg(b), ps[jj][1] = __ldg(b + 1);
+                    te[jj][0] = __ldg(c), te[jj][1] = __ldg(c + 1);
+                  }
+                }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                  const int idx = pl + kEGroup * (j0 + jj);
+                  float x[8];  // the sums replace the gathered dst rows register for register
+#pragma unroll
+                  for (int q = 0; q < 2; ++q) {
+                    x[4 * q] = (pd[jj][q].x + ps[jj][q].x) + te[jj][q].x;
+                    x[4 * q + 1] = (pd[jj][q].y + ps[jj][q].y) + te[jj][q].y;
+                    x[4 * q + 2] = (pd[jj][q].z + ps[jj][q].z) + te[jj][q].z;
+                    x[4 * q + 3] = (pd[jj][q].w + ps[jj][q].w) + te[jj][q].w;
+                  }
+                  if (kMode == 1) {
+                    // sign word of (edge, 32 hidden units) in the layout the dgrad epilogue reads: hidden unit u of the
+                    // chunk sits at bit (u & 3) * 8 + (u >> 2).  This slot holds u = (c & 3) * 8 + t, t = 0..7; the four
+                    // slots of a word live in four adjacent lanes.
+                    const int c = idx & 7;
+                    uint32_t part = 0;
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                      part |= (x[t] > 0.f ? 1u : 0u) << ((t & 3) * 8 + (c & 3) * 2 + (t >> 2));
+                    part |= __shfl_xor_sync(0xffffffffu, part, 1);
+                    part |= __shfl_xor_sync(0xffffffffu, part, 2);
+                    const int r = idx >> 3;
+                    if ((lane & 3) == 0 && r < nv)
+                      g.signs[((int64_t)(net * H + h) * (2 * kcn) + 2 * kc + (c >> 2)) * g.n_edges + e0 + r] = part;
+                  }
+#pragma unroll
+                  for (int t = 0; t < 8; ++t) x[t] = lrelu(x[t]) * kHidScale;
+                  uint4 hi, lo;
+                  split_f16x8s(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), 1.f, hi, lo);
+                  const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+                  *reinterpret_cast<uint4*>(bh + off) = hi;
+                  *reinterpret_cast<uint4*>(bh + kPackImageBytes + off) = lo;
+                }
               }
-              x.x = lrelu(x.x), x.y = lrelu(x.y), x.z = lrelu(x.z), x.w = lrelu(x.w);
-              float4 hi, lo;
-              split_tf32(x, hi, lo);
-              const uint32_t off = sw128_offset(idx >> 3, idx & 7);
-              *reinterpret_cast<float4*>(bh + off) = hi;
-              *reinterpret_cast<float4*>(bh + kPackImageBytes + off) = lo;
+            } else {
+              float4 pd[4], ps[4], te[4];
+              const int col0 = h * hd + kc * 32;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int cch = (pl + kEGroup * j) & 7;
+                const int col = col0 + cch * 4;
+                const bool ok = rd[j] >= 0 && (kc * 32 + cch * 4) < hd;
+                pd[j] = ps[j] = te[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok) {
+                  pd[j] = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)rd[j] * ldp + net * hhd + col));
+                  ps[j] = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)rs[j] * ldp + 2 * hhd + net * hhd + col));
+                  te[j] = __ldg(reinterpret_cast<const float4*>(g.T + (int64_t)rr[j] * ldt + net * hhd + col));
+                }
+              }
+              uint8_t* bh = st + kPackStageBytes;
+  #pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int idx = pl + kEGroup * j;
+                float4 x;
+                x.x = pd[j].x + ps[j].x + te[j].x;
+                x.y = pd[j].y + ps[j].y + te[j].y;
+                x.z = pd[j].z + ps[j].z + te[j].z;
+                x.w = pd[j].w + ps[j].w + te[j].w;
+                if (kMode == 1) {
+                  // which side of the LeakyReLU each hidden pre-activation is on: byte j' = component j' of the
+                  // float4, bit c = 16-byte chunk c of the 128-byte row  ->  hidden unit c*4 + j' of this K chunk
+                  const uint32_t b0 = __ballot_sync(0xffffffffu, x.x > 0.f), b1 = __ballot_sync(0xffffffffu, x.y > 0.f);
+                  const uint32_t b2 = __ballot_sync(0xffffffffu, x.z > 0.f), b3 = __ballot_sync(0xffffffffu, x.w > 0.f);
+                  const int sh = lane & 24;  // the 8 lanes that share an edge row
+                  const uint32_t word = ((b0 >> sh) & 0xFFu) | (((b1 >> sh) & 0xFFu) << 8) | (((b2 >> sh) & 0xFFu) << 16) |
+                                        (((b3 >> sh) & 0xFFu) << 24);
+                  const int r = idx >> 3;
+                  if ((lane & 7) == 0 && r < nv)
+                    g.signs[((int64_t)(net * H + h) * kcn + kc) * g.n_edges + e0 + r] = word;
+                }
+                x.x = lrelu(x.x), x.y = lrelu(x.y), x.z = lrelu(x.z), x.w = lrelu(x.w);
+                float4 hi, lo;
+                split_tf32(x, hi, lo);
+                const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+                *reinterpret_cast<float4*>(bh + off) = hi;
+                *reinterpret_cast<float4*>(bh + kPackImageBytes + off) = lo;
+              }
             }
             fence_async_smem();
             mbar_arrive(&full[s]);
@@ -365,7 +439,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     }
   } else {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc_tf32(kEF, kET);
+    constexpr uint32_t idesc = kF16 ? umma_idesc_f16(kEF, kET) : umma_idesc_tf32(kEF, kET);
     uint32_t cnt = 0, hcount = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
       for (int h = 0; h < H; ++h, ++hcount) {
@@ -384,9 +458,15 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t off = ks * 32;
-                umma_tf32(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-                umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-                umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+                if constexpr (kF16) {  // K = 16 halves = the same 32 bytes of the swizzled row
+                  umma_f16(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                  umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                  umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+                } else {
+                  umma_tf32(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                  umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                  umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+                }
               }
               umma_commit(&empty[s]);
               if (net == 1 && kc == kcn - 1) umma_commit(&tmem_full[hb]);
@@ -418,27 +498,30 @@ int check_edge_args(int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, 
   return 0;
 }
 
-template <int kMode>
+template <int kMode, bool kF16 = false>
 int launch_edge(const EdgeArgs& a, cudaStream_t stream) {
   static bool configured = false;
   if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(edge_attn_kernel<kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize, kESmemBytes));
+    CGAT_CUDA(cudaFuncSetAttribute(edge_attn_kernel<kMode, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kESmemBytes));
     configured = true;
   }
   const int64_t tiles = ceil_div(a.n_edges, kET);
   const int grid = (int)(tiles < kNumSMs ? tiles : kNumSMs);
-  edge_attn_kernel<kMode><<<grid, kEThreads, kESmemBytes, stream>>>(a);
+  edge_attn_kernel<kMode, kF16><<<grid, kEThreads, kESmemBytes, stream>>>(a);
   return check_launch(kMode == 0 ? "edge_attn_fwd_kernel" : "edge_attn_bwd_prep_kernel");
 }
 }  // namespace
 
-extern "C" int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
-                                  const int32_t* dst, const int32_t* rank, const float* w2a_packed,
-                                  const float* w2m_packed, const float* b2a, const float* b2m, float* out,
-                                  float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
-                                  int32_t f, int32_t hd, float eps, void* stream_) {
+namespace {
+template <bool kF16>
+int edge_fwd_impl(const float* P, const float* T, const int32_t* rowptr, const int32_t* src, const int32_t* dst,
+                  const int32_t* rank, const float* w2a_packed, const float* w2m_packed, const float* b2a,
+                  const float* b2m, float* out, float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges,
+                  int32_t heads, int32_t f, int32_t hd, float eps, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
+  if (kF16 && (hd & 63)) return fail(-2, "cgat_edge_attn_fwd_f16: hidden width must be a multiple of 64");
   if (n_atoms <= 0) return 0;
   const size_t out_bytes = sizeof(float) * (size_t)n_atoms * heads * f;
   CGAT_CUDA(cudaMemsetAsync(out, 0, out_bytes, stream));  // atoms without in-edges aggregate to 0
@@ -449,7 +532,43 @@ extern "C" int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t*
   if (n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
              nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
-  return launch_edge<0>(a, stream);
+  return launch_edge<0, kF16>(a, stream);
+}
+
+template <bool kF16>
+int edge_bwd_prep_impl(const float* P, const float* T, const int32_t* rowptr, const int32_t* src, const int32_t* dst,
+                       const int32_t* rank, const float* w2a_packed, const float* w2m_packed, const float* b2a,
+                       const float* b2m, const float* out, const float* seg_max, const float* seg_den,
+                       const float* g_out, float* d_gate, float* d_msg, uint32_t* signs, int64_t n_atoms,
+                       int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
+  if (kF16 && (hd & 63)) return fail(-2, "cgat_edge_attn_bwd_prep_f16: hidden width must be a multiple of 64");
+  if (n_atoms <= 0 || n_edges <= 0) return 0;
+  EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
+             const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs,
+             (int)n_atoms, (int)n_edges, heads, hd, eps};
+  return launch_edge<1, kF16>(a, stream);
+}
+}  // namespace
+
+extern "C" int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                                  const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                                  const float* w2m_packed, const float* b2a, const float* b2m, float* out,
+                                  float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                  int32_t f, int32_t hd, float eps, void* stream_) {
+  return edge_fwd_impl<false>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
+                              n_atoms, n_edges, heads, f, hd, eps, stream_);
+}
+
+// The same kernel on kind::f16 passes; w2a/w2m_packed = cgat_pack_kmajor_f16s(W2, pre_scale 64, lo_scale 1).
+extern "C" int cgat_edge_attn_fwd_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                                      const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                                      const float* w2m_packed, const float* b2a, const float* b2m, float* out,
+                                      float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                      int32_t f, int32_t hd, float eps, void* stream_) {
+  return edge_fwd_impl<true>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
+                             n_atoms, n_edges, heads, f, hd, eps, stream_);
 }
 
 // Backward, step 1: per-edge gradients of the second-layer outputs.  Recomputes a_t,h / v_t,h exactly like
@@ -461,11 +580,16 @@ extern "C" int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int
                                        const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
                                        float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
                                        int32_t f, int32_t hd, float eps, void* stream_) {
-  cudaStream_t stream = (cudaStream_t)stream_;
-  if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
-  if (n_atoms <= 0 || n_edges <= 0) return 0;
-  EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
-             const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs,
-             (int)n_atoms, (int)n_edges, heads, hd, eps};
-  return launch_edge<1>(a, stream);
+  return edge_bwd_prep_impl<false>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
+                                   g_out, d_gate, d_msg, signs, n_atoms, n_edges, heads, f, hd, eps, stream_);
+}
+
+extern "C" int cgat_edge_attn_bwd_prep_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                                       const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                                       const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
+                                       const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
+                                       float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                       int32_t f, int32_t hd, float eps, void* stream_) {
+  return edge_bwd_prep_impl<true>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
+                                  g_out, d_gate, d_msg, signs, n_atoms, n_edges, heads, f, hd, eps, stream_);
 }

@@ -112,34 +112,45 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
         const int o = chunk * oc + oi;
         const uint32_t b = ocount & 1u;
         const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
+        // The bias of the predicted weight row, p[n, o*F + j] = D_o[n, j] + bl[o*F + j], does not depend on the MMAs:
+        // its contribution is taken BEFORE waiting for the accumulator (broadcast loads: every thread of a column
+        // group reads the same 32 floats), so only tcgen05.ld + two FMAs per element sit behind the barrier.
+        float acc = 0.f;
+        if (w_bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(w_bias + (int64_t)o * F + grp * QF);
+#pragma unroll
+          for (int q = 0; q < QF / 4; ++q) {
+            const float4 b4 = __ldg(bp + q);
+            if (kMode == 0) {
+              acc = fmaf(b4.x, y[4 * q], acc), acc = fmaf(b4.y, y[4 * q + 1], acc);
+              acc = fmaf(b4.z, y[4 * q + 2], acc), acc = fmaf(b4.w, y[4 * q + 3], acc);
+            } else {
+              y[4 * q] = fmaf(b4.x, sc, y[4 * q]), y[4 * q + 1] = fmaf(b4.y, sc, y[4 * q + 1]);
+              y[4 * q + 2] = fmaf(b4.z, sc, y[4 * q + 2]), y[4 * q + 3] = fmaf(b4.w, sc, y[4 * q + 3]);
+            }
+          }
+        }
         mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
         tc_fence_after();
-        float acc = 0.f;
         const uint32_t tb = tmem + lane_base + b * 2 * F + grp * QF;
+        // 8 columns per batch (80 registers per thread with 21 warps, 32 of them hold the row values), software
+        // pipelined: the loads of batch cc+1 are in flight while batch cc is consumed.  v = hi*hi products,
+        // w = (hi*lo + lo*hi products) * 2^11.
+        float v[2][8], w[2][8];
+        tmem_ld8(tb, v[0]);
+        tmem_ld8(tb + F, w[0]);
 #pragma unroll
         for (int cc = 0; cc < QF / 8; ++cc) {
-          // 8 columns per batch: with 21 warps per CTA a thread has 80 registers, 32 of them hold the row values
-          float v[8], w[8];
-          tmem_ld8(tb + cc * 8, v);
-          tmem_ld8(tb + F + cc * 8, w);
           tmem_ld_wait();
-          // w = (hi*lo + lo*hi products) * 2^11: rescale; + the bias of the predicted weight row (broadcast loads)
-          if (w_bias != nullptr) {
-            const float4* bp = reinterpret_cast<const float4*>(w_bias + (int64_t)o * F + grp * QF + cc * 8);
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              const float4 b4 = __ldg(bp + q);
-              w[4 * q] = fmaf(w[4 * q], kF16LoInv, b4.x), w[4 * q + 1] = fmaf(w[4 * q + 1], kF16LoInv, b4.y);
-              w[4 * q + 2] = fmaf(w[4 * q + 2], kF16LoInv, b4.z), w[4 * q + 3] = fmaf(w[4 * q + 3], kF16LoInv, b4.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) w[j] *= kF16LoInv;
+          if (cc + 1 < QF / 8) {
+            tmem_ld8(tb + (cc + 1) * 8, v[(cc + 1) & 1]);
+            tmem_ld8(tb + F + (cc + 1) * 8, w[(cc + 1) & 1]);
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            if (kMode == 0) acc = fmaf(v[j] + w[j], y[cc * 8 + j], acc);
-            else y[cc * 8 + j] = fmaf(v[j] + w[j], sc, y[cc * 8 + j]);
+            const float t = fmaf(w[cc & 1][j], kF16LoInv, v[cc & 1][j]);
+            if (kMode == 0) acc = fmaf(t, y[cc * 8 + j], acc);
+            else y[cc * 8 + j] = fmaf(t, sc, y[cc * 8 + j]);
           }
         }
         tc_fence_before();

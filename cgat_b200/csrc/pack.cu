@@ -39,7 +39,7 @@ __global__ void pack_kmajor_kernel(const float* __restrict__ w, int64_t ld, int 
 
 // fp16 form (f16x3, tc_common.cuh): tiles of 128 rows x 64 halves; thread -> (row r, 16-byte chunk c = 8 halves)
 __global__ void pack_kmajor_f16_kernel(const float* __restrict__ w, int64_t ld, int rows, int k, int transpose,
-                                       float* __restrict__ out) {
+                                       float pre_scale, float lo_scale, float* __restrict__ out) {
   const int kc = blockIdx.x, rt = blockIdx.y;
   uint8_t* dst = reinterpret_cast<uint8_t*>(out) + ((int64_t)rt * gridDim.x + kc) * kPackStageBytes;
   for (int idx = threadIdx.x; idx < kPackRows * 8; idx += blockDim.x) {
@@ -54,10 +54,10 @@ __global__ void pack_kmajor_f16_kernel(const float* __restrict__ w, int64_t ld, 
         else if (transpose == 1) x = w[(int64_t)(gk + j) * ld + gr];
         else x = w[((int64_t)rt * kPackRows + gk + j) * ld + r];  // 2: transpose inside each 128 x 128 block
       }
-      v[j] = x;
+      v[j] = x * pre_scale;
     }
     uint4 hi, lo;
-    split_f16x8(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), hi, lo);
+    split_f16x8s(make_float4(v[0], v[1], v[2], v[3]), make_float4(v[4], v[5], v[6], v[7]), lo_scale, hi, lo);
     const uint32_t off = sw128_offset(r, c);
     *reinterpret_cast<uint4*>(dst + off) = hi;
     *reinterpret_cast<uint4*>(dst + kPackImageBytes + off) = lo;
@@ -85,14 +85,20 @@ extern "C" int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_
 
 extern "C" int64_t cgat_packed_floats_f16(int64_t rows, int64_t k) { return tc::packed_floats_f16(rows, k); }
 
-// fp16 hi/lo form of cgat_pack_kmajor (operands of the kind::f16 kernels): same arguments, `out` holds
-// cgat_packed_floats_f16(rows, k) floats.
-extern "C" int cgat_pack_kmajor_f16(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
-                                    void* stream_) {
+// fp16 hi/lo form of cgat_pack_kmajor (operands of the kind::f16 kernels): hi = f16(w * pre_scale),
+// lo = f16((w * pre_scale - hi) * lo_scale); `out` holds cgat_packed_floats_f16(rows, k) floats.
+extern "C" int cgat_pack_kmajor_f16s(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose,
+                                     float pre_scale, float lo_scale, float* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows <= 0 || k <= 0) return 0;
   if (transpose == 2 && (k != tc::kPackRows || rows % tc::kPackRows)) return fail(-2, "cgat_pack_kmajor_f16: block transpose needs 128 x 128 blocks");
   dim3 grid((unsigned)ceil_div(k, tc::kPackChunk16), (unsigned)ceil_div(rows, tc::kPackRows));
-  pack_kmajor_f16_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, out);
+  pack_kmajor_f16_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, pre_scale, lo_scale, out);
   return check_launch("pack_kmajor_f16_kernel");
+}
+
+// the form cgat_hyper_*_f16 read: unscaled hi, lo scaled by 2^11 (separate correction accumulator)
+extern "C" int cgat_pack_kmajor_f16(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
+                                    void* stream_) {
+  return cgat_pack_kmajor_f16s(w, ld, rows, k, transpose, 1.f, tc::kF16LoScale, out, stream_);
 }

@@ -284,20 +284,24 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
-// two fp32 -> packed (hi.x | hi.y << 16), (lo.x | lo.y << 16)
-__device__ __forceinline__ void split_f16x2(float x, float y, uint32_t& hi, uint32_t& lo) {
+// two fp32 -> packed (hi.x | hi.y << 16), (lo.x | lo.y << 16), lo = rn_f16((x - hi) * lo_scale)
+__device__ __forceinline__ void split_f16x2s(float x, float y, float lo_scale, uint32_t& hi, uint32_t& lo) {
   const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
-  const __half lx = __float2half_rn((x - __half2float(hx)) * kF16LoScale);
-  const __half ly = __float2half_rn((y - __half2float(hy)) * kF16LoScale);
+  const __half lx = __float2half_rn((x - __half2float(hx)) * lo_scale);
+  const __half ly = __float2half_rn((y - __half2float(hy)) * lo_scale);
   hi = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
   lo = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
 }
 // 8 consecutive fp32 (two float4) -> one 16-byte chunk of the hi image and one of the lo image
+__device__ __forceinline__ void split_f16x8s(const float4& a, const float4& b, float lo_scale, uint4& hi, uint4& lo) {
+  split_f16x2s(a.x, a.y, lo_scale, hi.x, lo.x);
+  split_f16x2s(a.z, a.w, lo_scale, hi.y, lo.y);
+  split_f16x2s(b.x, b.y, lo_scale, hi.z, lo.z);
+  split_f16x2s(b.z, b.w, lo_scale, hi.w, lo.w);
+}
+// the scaled-lo form used with a separate correction accumulator (hyper_f16.cu)
 __device__ __forceinline__ void split_f16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
-  split_f16x2(a.x, a.y, hi.x, lo.x);
-  split_f16x2(a.z, a.w, hi.y, lo.y);
-  split_f16x2(b.x, b.y, hi.z, lo.z);
-  split_f16x2(b.z, b.w, hi.w, lo.w);
+  split_f16x8s(a, b, kF16LoScale, hi, lo);
 }
 
 // Packed K-major fp16 operand: tiles of kPackRows rows x kPackChunk16 halves (128-byte rows, SWIZZLE_128B), stored

@@ -47,13 +47,22 @@ class GradSync:
         for p in self.params:
             p.grad = None
 
+    def pack(self):
+        """Gather the live gradients into the flat buffer and leave every p.grad as a view into it (capturable:
+        graphed.GraphedTrainStep records this at the end of its forward+backward graph)."""
+        grads = [p.grad.reshape(-1) if p.grad is not None else torch.zeros_like(p).reshape(-1) for p in self.params]
+        torch.cat(grads, out=self.flat)
+        for p, v in zip(self.params, self.flat.split(self.sizes)):
+            p.grad = v.view_as(p)
+
+    def reduce(self):
+        """One in-place NCCL all-reduce of the flat buffer, then the DDP average."""
+        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
+        self.flat.div_(self.world)
+
     def all_reduce(self):
         """Sum over ranks and divide by world size (DDP semantics). No-op for a single rank."""
         if self.world <= 1:
             return
-        grads = [p.grad.reshape(-1) if p.grad is not None else torch.zeros_like(p).reshape(-1) for p in self.params]
-        torch.cat(grads, out=self.flat)
-        dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=self.group)
-        self.flat.div_(self.world)
-        for p, v in zip(self.params, self.flat.split(self.sizes)):
-            p.grad = v.view_as(p)
+        self.pack()
+        self.reduce()

@@ -4,8 +4,10 @@ A default-config train step is ~230 launches of this library's kernels plus ~700
 them from Python takes about as long as the GPU needs to run them (profiles/: host enqueue 27 ms vs 31 ms of GPU
 time at 500 crystals).  The reference has the same structure through PyG / Lightning and no answer to it.  Here a
 step is captured ONCE per bucket signature (cgat_b200/batching.py pads ragged batches to bucket boundaries with a
-dummy crystal) — forward, loss, backward, gradient all-reduce and AdamW in one graph — and every later step of that
-bucket is three things: copy the batch into the graph's static input buffers, `cudaGraphLaunch`, read the loss.
+dummy crystal) — forward, loss, backward and AdamW in one graph — and every later step of that bucket is three
+things: copy the batch into the graph's static input buffers, `cudaGraphLaunch`, read the loss.  On more than one
+rank the graph ends after the gradients have been packed into the flat all-reduce buffer; the single NCCL
+all-reduce and the fused AdamW launch follow eagerly (two host calls per step).
 
 Rules the capture relies on (all checked by tests/test_gpu_model.py::test_graphed_step_matches_eager):
   * nothing in CGAtNet.forward / backward syncs with the host or has data-dependent shapes (GraphBatch.num_graphs is
@@ -62,14 +64,26 @@ class GraphedTrainStep:
         self.captures = 0
 
     # -- the step itself, as Python: used eagerly and under capture
-    def _body(self, sb, target):
+    def _multi(self):
+        return self.sync is not None and self.sync.world > 1
+
+    def _fwd_bwd(self, sb, target):
         out = self.model(sb.graph, sb.roost)
         n_real = sb.graph.num_graphs - 1
         loss = self.loss_fn(out[:n_real, :1], target[:n_real])
         loss.backward()
-        if self.sync is not None:
-            self.sync.all_reduce()
+        if self._multi():
+            self.sync.pack()             # live gradients -> the flat all-reduce buffer; p.grad = views into it
+        return out, loss
+
+    def _finish(self):
+        if self._multi():
+            self.sync.reduce()
         self.opt.step()
+
+    def _body(self, sb, target):
+        out, loss = self._fwd_bwd(sb, target)
+        self._finish()
         return out, loss
 
     def _drop_grads(self):
@@ -94,7 +108,9 @@ class GraphedTrainStep:
         slot.target.copy_(target, non_blocking=True)
         slot.graph.replay()
         self.replayed_launches += slot.launches
-        ops.invalidate_packed()          # the replay changed the weights behind Python's back
+        if self._multi():
+            self._finish()               # NCCL all-reduce + AdamW stay outside the graph on more than one rank
+        ops.invalidate_packed()          # the step changed the weights behind Python's back
         return slot.loss
 
     def _capture(self, sig, sb, target, dev):
@@ -106,8 +122,13 @@ class GraphedTrainStep:
         ops.invalidate_packed()          # the graph must contain its own pack launches
         slot.graph = torch.cuda.CUDAGraph()
         before = _lib.launch_count()
-        with torch.cuda.graph(slot.graph, pool=self.pool):
-            out, loss = self._body(slot.inputs, slot.target)
+        # several ranks: NCCL's watchdog thread polls CUDA events while we capture; thread-local mode keeps its calls
+        # from invalidating the capture (launches from the autograd thread into the capturing stream are still recorded)
+        mode = "thread_local" if self._multi() else "global"
+        with torch.cuda.graph(slot.graph, pool=self.pool, capture_error_mode=mode):
+            # one rank: the whole step; several ranks: forward + backward + gradient packing (the all-reduce and the
+            # optimizer follow eagerly after each replay, reading p.grad = views of the flat buffer)
+            out, loss = self._fwd_bwd(slot.inputs, slot.target) if self._multi() else self._body(slot.inputs, slot.target)
             slot.out, slot.loss = out.detach(), loss.detach()
         slot.launches = _lib.launch_count() - before
         if self.pool is None:

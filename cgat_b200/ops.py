@@ -82,6 +82,8 @@ _TN_WGRAD = os.environ.get("CGAT_B200_TN", "1") != "0"   # weight gradients on c
 _TRUNK = os.environ.get("CGAT_B200_TRUNK", "1") != "0"   # hypernetwork trunks: fused chain kernel vs library GEMMs
 # activation x weight tensor-core kernels on kind::f16 with scaled fp16 hi/lo operands (1) or kind::tf32 hi/lo (0)
 _F16X3 = os.environ.get("CGAT_B200_F16X3", "1") != "0"
+_F16X3_EDGE = os.environ.get("CGAT_B200_F16X3_EDGE", "1") != "0"   # the same for the edge-attention forward / bwd_prep
+_EDGE_W2_PRESCALE = 64.0   # cgat_edge_attn_*_f16 expect W2 packed as f16(w * 2^6) hi/lo with an unscaled lo
 
 
 def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
@@ -186,9 +188,12 @@ def gemm3x_tn(a, b, n_split=None):
     return part[0] if n_split == 1 else part.sum(dim=0)
 
 
-# Packed operand caches are keyed on the weight's autograd version.  A CUDA-graph replay updates weights without
-# Python seeing it, so cgat_b200/graphed.py bumps this epoch (a) before every capture of a training graph, which
-# makes the capture contain its own pack launches, and (b) after every replay, so eager code repacks too.
+# Packed operand caches are keyed on (the weight's autograd version, this epoch).  The version counter alone is
+# not enough: fused optimizers (torch.optim.AdamW(fused=True), i.e. torch._fused_adamw_) update parameters WITHOUT
+# bumping it, and a CUDA-graph replay updates them without Python running at all.  The epoch is bumped
+#   * after every torch.optim.Optimizer.step() in the process (global post-step hook, registered below),
+#   * by cgat_b200/graphed.py before every capture of a training graph (the capture then contains its own pack
+#     launches) and after every replay (so that eager code repacks too).
 _pack_epoch = 0
 
 
@@ -197,15 +202,25 @@ def invalidate_packed():
     _pack_epoch += 1
 
 
-def packed_kmajor(w, rows=None, transpose=False, f16=False):
+def _after_optimizer_step(optimizer, args, kwargs):
+    invalidate_packed()
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_step  # noqa: E402
+
+_register_post_step(_after_optimizer_step)
+
+
+def packed_kmajor(w, rows=None, transpose=False, f16=False, pre_scale=None):
     """Pre-split / pre-swizzled copy of w[:rows] (2-D view of a contiguous weight) for the fused
-    kernels (tf32 hi/lo images, or scaled fp16 hi/lo images with f16=True).  Cached ON the tensor object and
+    kernels: tf32 hi/lo images; with f16=True fp16 hi/lo images, either (hi, lo * 2^11) for the kernels with a
+    separate correction accumulator or, with pre_scale, (f16(w * pre_scale), unscaled lo).  Cached ON the tensor and
     keyed by its autograd version counter, so an in-place optimizer update (which bumps `_version`) triggers a
     repack and a freed tensor cannot leave a stale entry behind."""
     w2 = w.detach().view(w.shape[0], -1)
     rows = w2.shape[0] if rows is None else rows
     cache = w.__dict__.setdefault("_cgat_packed", {})
-    key = (rows, int(transpose), bool(f16))
+    key = (rows, int(transpose), bool(f16), pre_scale)
     hit = cache.get(key)
     if hit is not None and hit[0] == (w._version, _pack_epoch) and hit[2] == w.data_ptr():
         return hit[1]
@@ -213,9 +228,13 @@ def packed_kmajor(w, rows=None, transpose=False, f16=False):
     n_rows, k = (w2.shape[1], rows) if int(transpose) == 1 else (rows, w2.shape[1])
     size = lib.cgat_packed_floats_f16(n_rows, k) if f16 else lib.cgat_packed_floats(n_rows, k)
     buf = hit[1] if hit is not None else torch.empty(int(size), dtype=torch.float32, device=w.device)
-    _lib.call("cgat_pack_kmajor_f16" if f16 else "cgat_pack_kmajor", _lib.ptr(w2), w2.stride(0), n_rows, k,
-              int(transpose), _lib.ptr(buf), _lib.stream(),
-              work=dict(key="pack_kmajor", bound="hbm", bytes=(8.0 if f16 else 12.0) * n_rows * k))
+    work = dict(key="pack_kmajor", bound="hbm", bytes=(8.0 if f16 else 12.0) * n_rows * k)
+    if f16 and pre_scale is not None:
+        _lib.call("cgat_pack_kmajor_f16s", _lib.ptr(w2), w2.stride(0), n_rows, k, int(transpose), float(pre_scale), 1.0,
+                  _lib.ptr(buf), _lib.stream(), work=work)
+    else:
+        _lib.call("cgat_pack_kmajor_f16" if f16 else "cgat_pack_kmajor", _lib.ptr(w2), w2.stride(0), n_rows, k,
+                  int(transpose), _lib.ptr(buf), _lib.stream(), work=work)
     cache[key] = ((w._version, _pack_epoch), buf, w.data_ptr())
     return buf
 
@@ -475,8 +494,9 @@ class _EdgeAttentionFused(torch.autograd.Function):
     cgat_gemm3x_nt / cgat_gemm3x_tn.  Deterministic, atomic-free."""
 
     @staticmethod
-    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads):
+    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads, f16):
         x, edge_table = _f32c(x), _f32c(edge_table)
+        ctx.f16 = f16
         n, f = x.shape
         fe = edge_table.shape[1]
         hhd = w1a.shape[0]
@@ -490,13 +510,15 @@ class _EdgeAttentionFused(torch.autograd.Function):
         sden = torch.empty_like(out) if train else None
         e = plan.n_edges
         b2a, b2m = b2a.contiguous(), b2m.contiguous()
-        _lib.call("cgat_edge_attn_fwd", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
+        _lib.call("cgat_edge_attn_fwd_f16" if f16 else "cgat_edge_attn_fwd", _lib.ptr(P), _lib.ptr(T),
+                  _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed),
                   _lib.ptr(b2a), _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden),
                   n, e, heads, f, hd, 1e-16, _lib.stream(),
                   work=dict(key="edge_attn_fwd", bound="tensor", flops=2.0 * e * heads * hd * 2 * f,
                             bytes=4.0 * (e * (3 + 2 * 2 * hhd) + n * heads * f),
-                            note="second MLP layer (E x Hd x F per head, gate+message) on tcgen05, 3xTF32"))
+                            note="second MLP layer (E x Hd x F per head, gate+message) on tcgen05, "
+                                 + ("f16x3" if f16 else "3xTF32")))
         if train:
             ctx.save_for_backward(x, edge_table, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax,
                                   sden, w_atom_t, w_rank)
@@ -523,7 +545,8 @@ class _EdgeAttentionFused(torch.autograd.Function):
         d_msg = torch.empty_like(d_gate)
         signs = torch.empty(2 * heads * kcn * max(e, 1), dtype=torch.int32, device=dev)
         flops2 = 2.0 * e * heads * hd * 2 * f
-        _lib.call("cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
+        _lib.call("cgat_edge_attn_bwd_prep_f16" if ctx.f16 else "cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T),
+                  _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed), _lib.ptr(b2a),
                   _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(g), _lib.ptr(d_gate),
                   _lib.ptr(d_msg), _lib.ptr(signs), n, e, heads, f, hd, 1e-16, st,
@@ -566,7 +589,8 @@ class _EdgeAttentionFused(torch.autograd.Function):
         g_b1 = d_t.sum(dim=0)
         g_w1a = torch.cat([g_watom[:hhd], g_wrank[:hhd], g_watom[2 * hhd:3 * hhd]], dim=1).reshape(w1a.shape)
         g_w1m = torch.cat([g_watom[hhd:2 * hhd], g_wrank[hhd:], g_watom[3 * hhd:]], dim=1).reshape(w1m.shape)
-        return (g_x, g_tab, g_w1a, g_b1[:hhd], g_w2a, g_b2a, g_w1m, g_b1[hhd:], g_w2m, g_b2m, None, None, None, None)
+        return (g_x, g_tab, g_w1a, g_b1[:hhd], g_w2a, g_b2a, g_w1m, g_b1[hhd:], g_w2m, g_b2m, None, None, None, None,
+                None)
 
 
 def edge_attention_heads_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
@@ -599,10 +623,12 @@ def edge_attention(x, edge_table, plan, mh_a, mh_m, heads):
                 and hd % 128 == 0 and hd <= 256 and heads <= 8 and edge_table.shape[1] % 4 == 0
                 and edge_table.shape[0] <= 32)
     if fused_ok:
+        f16 = _F16X3_EDGE and hd % 64 == 0
+        pk = dict(f16=True, pre_scale=_EDGE_W2_PRESCALE) if f16 else {}
         out = _EdgeAttentionFused.apply(x, edge_table, mh_a.fc_in.weight, mh_a.fc_in.bias, mh_a.fc_out.weight,
                                         mh_a.fc_out.bias, mh_m.fc_in.weight, mh_m.fc_in.bias, mh_m.fc_out.weight,
-                                        mh_m.fc_out.bias, packed_kmajor(mh_a.fc_out.weight),
-                                        packed_kmajor(mh_m.fc_out.weight), plan, heads)
+                                        mh_m.fc_out.bias, packed_kmajor(mh_a.fc_out.weight, **pk),
+                                        packed_kmajor(mh_m.fc_out.weight, **pk), plan, heads, f16)
         return out.mean(dim=1)
     return edge_attention_unfused(x, edge_table, plan, mh_a.w_in(), mh_a.fc_in.bias, mh_a.w_out(), mh_a.fc_out.bias,
                                   mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads)

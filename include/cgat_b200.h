@@ -115,6 +115,10 @@ int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_
 int64_t cgat_packed_floats_f16(int64_t rows, int64_t k);
 int cgat_pack_kmajor_f16(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
                          void* stream);
+/* General form: hi = f16(w * pre_scale), lo = f16((w * pre_scale - hi) * lo_scale).  cgat_pack_kmajor_f16 is
+ * (1, 2^11); the edge-attention kernels, whose three products share one accumulator, read (2^6, 1).          */
+int cgat_pack_kmajor_f16s(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float pre_scale,
+                          float lo_scale, float* out, void* stream);
 
 /* ---- fused hypernetwork linear layer ----------------------------------
  * y_out[n,o] = sum_i (sum_k z[n,k] W[o*F+i,k] + w_bias[o*F+i]) * y_in[n,i] + e_term[n,o]
@@ -160,6 +164,13 @@ int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, co
                        const float* w2m_packed, const float* b2a, const float* b2m, float* out,
                        float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
                        int32_t f, int32_t hd, float eps, void* stream);
+/* The same kernel on kind::f16 passes (half the W2 stream from L2, twice the tensor rate): identical arguments and
+ * results; w2a/w2m_packed = cgat_pack_kmajor_f16s(W2, .., pre_scale 64, lo_scale 1); Hd % 64 == 0.          */
+int cgat_edge_attn_fwd_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                           const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                           const float* w2m_packed, const float* b2a, const float* b2m, float* out,
+                           float* seg_max, float* seg_den, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                           int32_t f, int32_t hd, float eps, void* stream);
 
 /* Backward companion of cgat_hyper_rowdot_fwd (activation gradients):
  *   partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m] + w_bias[o*F+j]);  result =
@@ -198,6 +209,13 @@ int cgat_hyper_wgrad(const float* g, const float* y, const float* z, float* out,
  *         (cgat_edge_attn_wgrad_splits(H), 2, H, F, Hd).
  * Together they replace autograd through index_select / grouped Conv1d / softmax / scatter_add.     */
 int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
+                            const int32_t* dst, const int32_t* rank, const float* w2a_packed,
+                            const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
+                            const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
+                            float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                            int32_t f, int32_t hd, float eps, void* stream);
+/* kind::f16 form of cgat_edge_attn_bwd_prep (w2*_packed as for cgat_edge_attn_fwd_f16). */
+int cgat_edge_attn_bwd_prep_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
                             const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                             const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                             const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,

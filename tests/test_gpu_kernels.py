@@ -153,10 +153,12 @@ def test_pack_repack_on_weight_update():
 
 @pytest.mark.parametrize("n_cry,k,heads,lo,hi", [(3, 12, 5, 2, 20), (40, 12, 5, 2, 20), (2, 24, 2, 200, 256),
                                                  (700, 12, 5, 2, 20), (1, 4, 1, 2, 3)])
-def test_edge_attention_fused_matches_oracle(n_cry, k, heads, lo, hi):
-    """cgat_edge_attn_fwd (+ projection GEMMs) against the reference arithmetic of
-    GATConvNodes.message/aggregate (reference CGAT/CGAT.py:319-329) restated in fp64."""
+@pytest.mark.parametrize("f16", [True, False], ids=["f16x3", "tf32x3"])
+def test_edge_attention_fused_matches_oracle(n_cry, k, heads, lo, hi, f16, monkeypatch):
+    """cgat_edge_attn_fwd[_f16] (+ projection GEMMs) against the reference arithmetic of
+    GATConvNodes.message/aggregate (reference CGAT/CGAT.py:319-329) restated in fp64; both operand formats."""
     from cgat_b200.CGAT import MultiHeadNetwork
+    monkeypatch.setattr(ops, "_F16X3_EDGE", f16)
     f, fe = 128, 128
     sb = synthetic.make_batch(n_cry, k, seed=n_cry, atoms_lo=lo, atoms_hi=hi)
     gidx = sb.graph
@@ -198,9 +200,11 @@ def test_edge_attention_fused_matches_oracle(n_cry, k, heads, lo, hi):
 
 @pytest.mark.parametrize("n_cry,k,heads,lo,hi", [(3, 12, 5, 2, 20), (60, 12, 5, 2, 20), (2, 24, 2, 200, 256),
                                                  (500, 12, 5, 2, 20)])
-def test_edge_attention_fused_backward_all_grads(n_cry, k, heads, lo, hi):
+@pytest.mark.parametrize("f16", [True, False], ids=["f16x3", "tf32x3"])
+def test_edge_attention_fused_backward_all_grads(n_cry, k, heads, lo, hi, f16, monkeypatch):
     """Fused edge-attention backward (bwd_prep + dgrad x2 + wgrad + first-layer GEMMs): every gradient
     against autograd through the fp64 restatement of GATConvNodes.message/aggregate."""
+    monkeypatch.setattr(ops, "_F16X3_EDGE", f16)
     from cgat_b200.CGAT import MultiHeadNetwork
     from tests._cases import assert_grad_close
     f, fe = 128, 128

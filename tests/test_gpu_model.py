@@ -128,6 +128,31 @@ def _train_setup(seed=0):
     return model, opt
 
 
+def test_fused_optimizer_updates_reach_the_packed_operands():
+    """Three eager train steps with AdamW(fused=True) — which does not bump parameter version counters — follow the
+    same trajectory as AdamW(foreach=True), i.e. the pre-packed tensor-core operands are rebuilt after every step."""
+    from cgat_b200 import distributed as cdist
+    crit = torch.nn.L1Loss()
+    batches = [synthetic.make_batch(40, 12, seed=s).to(DEV) for s in (1, 2, 3)]
+    losses = {}
+    for kind in ("fused", "foreach"):
+        mkw = CASES["default_k12"][0]
+        model = weights.load_seeded(cgat_b200.CGAtNet(200, **mkw), 0).to(DEV)
+        opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-6, **{kind: True})
+        sync = cdist.GradSync(model, 1)
+        losses[kind] = []
+        for d in batches:
+            y = d.graph.y
+            loss = crit(model(d.graph, d.roost)[:, :1], (y / y.abs().max()).view(-1, 1))
+            loss.backward()
+            opt.step()
+            sync.zero_grad()
+            losses[kind].append(float(loss))
+    for i, (a, b) in enumerate(zip(losses["fused"], losses["foreach"])):
+        assert abs(a - b) <= 1e-5 + 1e-4 * abs(b), f"step {i}: fused {a} vs foreach {b}"
+    assert abs(losses["fused"][1] - losses["fused"][0]) > 0
+
+
 def test_graphed_step_matches_eager():
     """graphed.GraphedTrainStep (one CUDA graph per shape bucket: forward, loss, backward, AdamW) follows the eager
     loop step for step: same losses and same weights after steps that cross two buckets and revisit the first."""

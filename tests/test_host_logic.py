@@ -112,3 +112,15 @@ def test_padding_is_invisible(emulated_kernels):
     assert g_ref.keys() == g_pad.keys()
     for k in g_ref:
         assert_close(g_pad[k], g_ref[k], f"padded grad {k}", atol=1e-6, rtol=1e-5)
+
+
+def test_optimizer_step_invalidates_packed_operands():
+    """torch's fused optimizers update parameters without bumping the autograd version counter the packed-operand
+    caches are keyed on; the global post-step hook in cgat_b200.ops must invalidate them instead."""
+    from cgat_b200 import ops
+    p = [torch.nn.Parameter(torch.randn(4, 4))]
+    p[0].grad = torch.randn(4, 4)
+    for kw in (dict(fused=True), dict(foreach=True)):
+        before = ops._pack_epoch
+        torch.optim.AdamW(p, lr=1e-3, **kw).step()
+        assert ops._pack_epoch > before, f"AdamW({kw}).step() did not invalidate the packed operands"
