@@ -255,11 +255,12 @@ def run_ours(args):
     print(json.dumps(line))
 
 
-KERNEL_NAMES = {  # profile key (ops.py `work`) -> kernel name in the ncu capture (profiles/*_kernel_metrics.json)
-    "hyper_rowscale": "hyper_rowdot_fwd_kernel<128, 1>", "hyper_rowdot_fwd": "hyper_rowdot_fwd_kernel<128, 0>",
+KERNEL_NAMES = {  # profile key (ops.py `work`) -> kernel names in the ncu capture (profiles/*_kernel_metrics.json)
+    "hyper_rowscale": ["hyper_rowdot_f16_kernel<128, 1>", "hyper_rowdot_fwd_kernel<128, 1>"],
+    "hyper_rowdot_fwd": ["hyper_rowdot_f16_kernel<128, 0>", "hyper_rowdot_fwd_kernel<128, 0>"],
     "hyper_wgrad": "hyper_wgrad_kernel", "hyper_trunk_fwd": "hyper_trunk_kernel<0>",
-    "hyper_trunk_bwd": "hyper_trunk_kernel<1>", "edge_attn_fwd": "edge_attn_kernel<0>",
-    "edge_attn_bwd_prep": "edge_attn_kernel<1>", "edge_attn_dgrad": "edge_dgrad_kernel",
+    "hyper_trunk_bwd": "hyper_trunk_kernel<1>", "edge_attn_fwd": ["edge_attn_kernel<0, 1>", "edge_attn_kernel<0, 0>"],
+    "edge_attn_bwd_prep": ["edge_attn_kernel<1, 1>", "edge_attn_kernel<1, 0>"], "edge_attn_dgrad": "edge_dgrad_kernel",
     "edge_attn_wgrad": "edge_wgrad_kernel", "edge_attn_reduce": "edge_reduce_kernel",
     "gemm3x_nt": "gemm3x_nt_kernel<128>", "gemm3x_nt_res": "gemm3x_nt_res_kernel", "gemm3x_tn": "gemm3x_tn_kernel",
     "gemm3x_tn_batched": "gemm3x_tn_kernel",
@@ -273,8 +274,12 @@ def ncu_traffic(key, workload):
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", f"*_{workload}_kernel_metrics.json")))
     if not files:
         return None, None
-    m = json.load(open(files[-1])).get(KERNEL_NAMES.get(key, key))
-    return (m["traffic_bytes"], os.path.relpath(files[-1], ROOT)) if m else (None, None)
+    table = json.load(open(files[-1]))
+    names = KERNEL_NAMES.get(key, key)
+    for name in ([names] if isinstance(names, str) else names):   # first = the default (f16x3) kernel of the op
+        if name in table:
+            return table[name]["traffic_bytes"], os.path.relpath(files[-1], ROOT)
+    return None, None
 
 
 def roofline(model, sb, tgt, train, step, args):
@@ -310,9 +315,12 @@ def roofline(model, sb, tgt, train, step, args):
            "own_kernels_ms_per_step": round(total / n, 4), "own_kernel_shares": shares,
            "note": top.get("note", "")}
     if bound == "tensor":
-        # fp32 parity needs three TF32 passes per product: the same launch as tensor-pipe work
-        out["tf32_pass_tflops"] = round(3 * achieved, 2)
-        out["frac_of_3xtf32_ceiling"] = round(3 * achieved / (pk["bf16_sustained"] / 2), 4)
+        # fp32 parity needs three tensor passes per product: kind::f16 passes (the bf16 rate)
+        # for the f16x3 kernels, kind::tf32 passes (half that rate) for the others
+        f16 = top.get("note", "").startswith("f16x3") or "f16x3" in top.get("note", "")
+        out["tensor_pass_tflops"] = round(3 * achieved, 2)
+        out["pass_format"] = "f16" if f16 else "tf32"
+        out["frac_of_3pass_ceiling"] = round(3 * achieved / (pk["bf16_sustained"] / (1 if f16 else 2)), 4)
     return out
 
 

@@ -39,7 +39,7 @@ SIGNATURES = {
     "cgat_pack_kmajor_f16s": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _F32, _F32, _P, _P]),
     "cgat_edge_attn_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                               _I32, _I32, _F32, _P]),
-    "cgat_edge_attn_bwd_prep_f16": (ctypes.c_int, [_P] * 17 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_bwd_prep_f16": (ctypes.c_int, [_P] * 18 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
     "cgat_hyper_rowdot_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowscale_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
@@ -54,7 +54,8 @@ SIGNATURES = {
     "cgat_hyper_wgrad": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_edge_attn_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                           _I32, _I32, _F32, _P]),
-    "cgat_edge_attn_bwd_prep": (ctypes.c_int, [_P] * 17 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_bwd_prep": (ctypes.c_int, [_P] * 18 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_grid": (_I32, [_I64]),
     "cgat_edge_attn_dgrad_grid": (_I32, [_I64]),
     "cgat_edge_attn_dgrad": (ctypes.c_int, [_P] * 10 + [_I64, _I32, _P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P]),
     "cgat_edge_attn_reduce_chunks": (_I32, [_I64]),

@@ -297,20 +297,29 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
           const int r = (pt + kBProducers * j) >> 3;
           rowoff[j] = (r < nv) ? ((int64_t)mt[kBT + r] * H + h) * kBF : -1;  // padding rows are staged as zeros
         }
+        // the dZ rows of K chunk kc+1 are requested before this thread waits for the stage of chunk kc, so the
+        // L2 / HBM latency of the loads overlaps the wait and the conversion (was: load -> wait for data -> convert)
+        float4 x[4], nx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int cch = (pt + kBProducers * j) & 7;
+          x[j] = rowoff[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(dz[net] + rowoff[j] + cch * 4))
+                                : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
         for (int kc = 0; kc < kcf; ++kc, ++cnt) {
           const uint32_t s = cnt % kBStages, u = cnt / kBStages;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cch = (pt + kBProducers * j) & 7;
+            nx[j] = (kc + 1 < kcf && rowoff[j] >= 0)
+                        ? __ldg(reinterpret_cast<const float4*>(dz[net] + rowoff[j] + (kc + 1) * 32 + cch * 4))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           mbar_wait(&empty[s], (u + 1) & 1u);
           uint8_t* st = stages + s * kBStageBytes;
           if (pt == 0) {
             mbar_expect_tx(&full[s], kPackStageBytes);
             bulk_g2s(st, wt[net] + ((int64_t)(h * nhalf + half) * kcf + kc) * kPackStageBytes, kPackStageBytes, &full[s]);
-          }
-          float4 x[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const int cch = (pt + kBProducers * j) & 7;
-            x[j] = rowoff[j] >= 0 ? __ldg(reinterpret_cast<const float4*>(dz[net] + rowoff[j] + kc * 32 + cch * 4))
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
           }
           uint8_t* bh = st + kPackStageBytes;
 #pragma unroll
@@ -324,6 +333,8 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
           }
           fence_async_smem();
           mbar_arrive(&full[s]);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) x[j] = nx[j];
         }
       }
     }
@@ -469,7 +480,8 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArg
       }
       // B operand: hidden activations (32 edges x Hd), re-gathered like the forward
       uint8_t* bh = st + 2 * kWAPart;
-#pragma unroll 2
+      // 4 slots = 12 gathered float4 in flight per thread (13 warps per CTA leave 128 registers per thread)
+#pragma unroll 4
       for (int j = 0; j < 8; ++j) {
         const int idx = pt + kBProducers * j, r = idx >> 6, q = idx & 63;
         const int d = mt[r];

@@ -66,6 +66,7 @@ struct EdgeArgs {
   float* d_gate;        // backward-prep: dL/d a_t,h (E, H, F), destination-sorted edge order
   float* d_msg;         // backward-prep: dL/d v_t,h (E, H, F)
   uint32_t* signs;      // backward-prep: [2][H][kcn][E] LeakyReLU side of the 32 hidden units of a chunk
+  float* bias_sums;     // backward-prep (optional): (grid, 2, H, F) per-CTA column sums of d_msg | d_gate = dL/d b2
   int n_atoms, n_edges, heads, hd;
   float eps;
 };
@@ -159,6 +160,11 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     range[1] = g.rowptr[a_hi];
   }
   if (warp == kEMmaWarp) tmem_alloc(tmem_slot, 512);
+  if (kMode == 1 && tid < kEEpilogue) {
+    // backward-prep does not carry softmax state across tiles; the buffer holds the per-CTA column sums of
+    // d_msg / d_gate instead (the bias gradients of the second layer): [epilogue group][d_msg | d_gate][head][channel]
+    for (int i = tid; i < kECarryBytes / 4; i += kEEpilogue) carry[i] = 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -252,6 +258,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
         } else {
           float* pg = g.d_gate + (int64_t)e0 * hf + hc;
           float* pm = g.d_msg + (int64_t)e0 * hf + hc;
+          float sum_m = 0.f, sum_g = 0.f;  // this tile's column sums of d_msg / d_gate for (head h, channel c)
 #pragma unroll 1
           for (int cc = 0; cc < kET / 8; ++cc) {
             // per-segment statistics re-read per column: same address for the ~max_nbr edges of a segment, so these
@@ -274,13 +281,18 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               const float alpha = fast_exp(a - sm[j]) * fast_rcp(sd[j] + g.eps);
               const float ag = alpha * sg_[j];
               if ((valid >> j) & 1u) {
+                const float dg = ag * (v - so[j]);
                 pm[(int64_t)(cc * 8 + j) * hf] = ag;
-                pg[(int64_t)(cc * 8 + j) * hf] = ag * (v - so[j]);
+                pg[(int64_t)(cc * 8 + j) * hf] = dg;
+                sum_m += ag, sum_g += dg;
               }
             }
           }
           tc_fence_before();
           mbar_arrive(&tmem_empty[hb]);
+          // only this thread ever touches these two words: group grp handles its items one after the other
+          carry[((grp * 2 + 0) * kEMaxHeads + h) * kEF + c] += sum_m;
+          carry[((grp * 2 + 1) * kEMaxHeads + h) * kEF + c] += sum_g;
         }
       }
     }
@@ -337,19 +349,19 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                 float4 pd[2][2], ps[2][2], te[2][2];
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
-                  const int j = j0 + jj;
-                  const int cch = (pl + kEGroup * j) & 7;
+                  const int idx = pl + kEGroup * (j0 + jj);
+                  const int r = idx >> 3, cch = idx & 7;
                   const int col = col0 + cch * 8;
-                  const bool ok = rd[j] >= 0 && (kc * kPackChunk16 + cch * 8) < hd;
+                  // row ids straight from the tile metadata in shared memory (a register array indexed by the
+                  // loop counter would live in local memory: ncu r01h showed 16 % of the samples waiting on it)
+                  const int d = mt[r];
+                  const bool ok = d >= 0 && (kc * kPackChunk16 + cch * 8) < hd;
 #pragma unroll
                   for (int q = 0; q < 2; ++q) pd[jj][q] = ps[jj][q] = te[jj][q] = make_float4(0.f, 0.f, 0.f, 0.f);
                   if (ok) {
-                    const float4* a = reinterpret_cast<const float4*>(g.P + (int64_t)rd[j] * ldp + net * hhd + col);
-                    const float4* b = reinterpret_cast<const float4*>(g.P + (int64_t)rs[j] * ldp + 2 * hhd + net * hhd + col);
-                    const float4* c = reinterpret_cast<const float4*>(g.T + (int64_t)rr[j] * ldt + net * hhd + col);
-                    pd[jj][0] = __ldg(a), pd[jj][1] = __ldg(a + 1);
-                    ps[jj][0] = __ldg(b), ps[jj][1] = __ldg(b + 1);
-                    te[jj][0] = __ldg(c), te[jj][1] = __ldg(c + 1);
+                    ldg_v8(g.P + (int64_t)d * ldp + net * hhd + col, pd[jj][0], pd[jj][1]);
+                    ldg_v8(g.P + (int64_t)mt[kET + r] * ldp + 2 * hhd + net * hhd + col, ps[jj][0], ps[jj][1]);
+                    ldg_v8(g.T + (int64_t)mt[2 * kET + r] * ldt + net * hhd + col, te[jj][0], te[jj][1]);
                   }
                 }
 #pragma unroll
@@ -478,6 +490,13 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     }
   }
   __syncthreads();
+  if (kMode == 1 && g.bias_sums != nullptr) {
+    float* dst = g.bias_sums + (int64_t)blockIdx.x * 2 * H * kEF;
+    for (int i = tid; i < 2 * H * kEF; i += kEThreads) {
+      const int which = i / (H * kEF), hc = i - which * H * kEF, h = hc / kEF, c = hc - h * kEF;
+      dst[i] = carry[((0 * 2 + which) * kEMaxHeads + h) * kEF + c] + carry[((1 * 2 + which) * kEMaxHeads + h) * kEF + c];
+    }
+  }
   if (warp == kEMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
@@ -531,7 +550,7 @@ int edge_fwd_impl(const float* P, const float* T, const int32_t* rowptr, const i
   }
   if (n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-             nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
+             nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
   return launch_edge<0, kF16>(a, stream);
 }
 
@@ -539,18 +558,25 @@ template <bool kF16>
 int edge_bwd_prep_impl(const float* P, const float* T, const int32_t* rowptr, const int32_t* src, const int32_t* dst,
                        const int32_t* rank, const float* w2a_packed, const float* w2m_packed, const float* b2a,
                        const float* b2m, const float* out, const float* seg_max, const float* seg_den,
-                       const float* g_out, float* d_gate, float* d_msg, uint32_t* signs, int64_t n_atoms,
-                       int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps, void* stream_) {
+                       const float* g_out, float* d_gate, float* d_msg, uint32_t* signs, float* bias_sums,
+                       int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps,
+                       void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
   if (kF16 && (hd & 63)) return fail(-2, "cgat_edge_attn_bwd_prep_f16: hidden width must be a multiple of 64");
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
-             const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs,
+             const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs, bias_sums,
              (int)n_atoms, (int)n_edges, heads, hd, eps};
   return launch_edge<1, kF16>(a, stream);
 }
 }  // namespace
+
+// number of CTAs cgat_edge_attn_bwd_prep launches = rows of its bias_sums output
+extern "C" int32_t cgat_edge_attn_grid(int64_t n_edges) {
+  const int64_t tiles = ceil_div(n_edges, kET);
+  return (int32_t)(tiles < kNumSMs ? (tiles > 0 ? tiles : 1) : kNumSMs);
+}
 
 extern "C" int cgat_edge_attn_fwd(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
                                   const int32_t* dst, const int32_t* rank, const float* w2a_packed,
@@ -578,18 +604,18 @@ extern "C" int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int
                                        const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                                        const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                                        const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                                       float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                       float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
                                        int32_t f, int32_t hd, float eps, void* stream_) {
   return edge_bwd_prep_impl<false>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-                                   g_out, d_gate, d_msg, signs, n_atoms, n_edges, heads, f, hd, eps, stream_);
+                                   g_out, d_gate, d_msg, signs, bias_sums, n_atoms, n_edges, heads, f, hd, eps, stream_);
 }
 
 extern "C" int cgat_edge_attn_bwd_prep_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
                                        const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                                        const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                                        const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                                       float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                       float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
                                        int32_t f, int32_t hd, float eps, void* stream_) {
   return edge_bwd_prep_impl<true>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-                                  g_out, d_gate, d_msg, signs, n_atoms, n_edges, heads, f, hd, eps, stream_);
+                                  g_out, d_gate, d_msg, signs, bias_sums, n_atoms, n_edges, heads, f, hd, eps, stream_);
 }

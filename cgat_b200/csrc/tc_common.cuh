@@ -204,6 +204,14 @@ __device__ __forceinline__ void st_global_v8(float* p, const float* v) {
                : "memory");
 }
 
+// 32-byte read-only load (sm_100: LDG.256): 8 consecutive floats of a gathered row in one request, whole sectors.
+// p must be 32-byte aligned.
+__device__ __forceinline__ void ldg_v8(const float* p, float4& a, float4& b) {
+  asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+               : "l"(p));
+}
+
 // ---- fp32 -> tf32 hi/lo split -------------------------------------------------------------------
 // hi = round-to-nearest TF32 of x, lo = round-to-nearest TF32 of (x - hi) (the subtraction is exact in
 // fp32).  Both are exactly representable in TF32, so the tensor core's own operand conversion

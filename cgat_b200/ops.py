@@ -545,11 +545,13 @@ class _EdgeAttentionFused(torch.autograd.Function):
         d_msg = torch.empty_like(d_gate)
         signs = torch.empty(2 * heads * kcn * max(e, 1), dtype=torch.int32, device=dev)
         flops2 = 2.0 * e * heads * hd * 2 * f
+        # per-CTA column sums of d_msg | d_gate (the second-layer bias gradients) come out of the same kernel
+        bsum = torch.empty((int(lib.cgat_edge_attn_grid(e)), 2, heads, f), dtype=torch.float32, device=dev)
         _lib.call("cgat_edge_attn_bwd_prep_f16" if ctx.f16 else "cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T),
                   _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed), _lib.ptr(b2a),
                   _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(g), _lib.ptr(d_gate),
-                  _lib.ptr(d_msg), _lib.ptr(signs), n, e, heads, f, hd, 1e-16, st,
+                  _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(bsum), n, e, heads, f, hd, 1e-16, st,
                   work=dict(key="edge_attn_bwd_prep", bound="tensor", flops=flops2))
         # 2. dgrad on the tensor cores -> per-edge d_pre, then its per-destination / per-source / per-rank sums
         #    (HBM-bound, cgat_edge_attn_reduce)
@@ -580,7 +582,8 @@ class _EdgeAttentionFused(torch.autograd.Function):
                   work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2))
         d_w2 = part.sum(dim=0)
         g_w2a, g_w2m = d_w2[0].reshape(w2a.shape), d_w2[1].reshape(w2m.shape)
-        g_b2a, g_b2m = d_gate.sum(dim=0).reshape(-1), d_msg.sum(dim=0).reshape(-1)
+        g_b2 = bsum.sum(dim=0)
+        g_b2m, g_b2a = g_b2[0].reshape(-1), g_b2[1].reshape(-1)
         # 4. first layer: P = x w_atom^T, T = tab w_rank^T + b1
         g_x = gemm3x_splitk(d_p, w_atom_t)
         g_watom = gemm3x_tn(d_p, x)                                                 # (4*HHd, F)

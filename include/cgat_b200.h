@@ -212,14 +212,17 @@ int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int32_t* rowpt
                             const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                             const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                             const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                            float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                            float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
                             int32_t f, int32_t hd, float eps, void* stream);
+/* bias_sums (optional): (cgat_edge_attn_grid(E), 2, H, F) per-CTA column sums of d_msg | d_gate; their sum over
+ * dim 0 is dL/d b2 of the message | gate net, so the caller never re-reads the (E, H, F) tensors for it.       */
+int32_t cgat_edge_attn_grid(int64_t n_edges);
 /* kind::f16 form of cgat_edge_attn_bwd_prep (w2*_packed as for cgat_edge_attn_fwd_f16). */
 int cgat_edge_attn_bwd_prep_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
                             const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                             const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                             const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                            float* d_msg, uint32_t* signs, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                            float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
                             int32_t f, int32_t hd, float eps, void* stream);
 int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges);
 int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t* signs, const int32_t* segptr,
