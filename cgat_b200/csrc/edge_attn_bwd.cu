@@ -452,16 +452,23 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArg
   } else if (warp < 12) {
     const int pt = tid - 128;
     const float* dz = net ? g.d_msg : g.d_gate;
+    // The edge ids of chunk ch+1 are fetched while chunk ch is being staged (they used to cost one exposed L2 round
+    // trip per chunk, in front of the gathers that depend on them); threads 0-31 carry them in registers.
+    int nd = -1, ns = 0, nr = 0;
+    if (pt < 32 && n_chunks > 0) {
+      const bool ok = pt < min(32, e_hi - e_lo);
+      nd = ok ? g.dst[e_lo + pt] : -1, ns = ok ? g.src[e_lo + pt] : 0, nr = ok ? g.rank[e_lo + pt] : 0;
+    }
     for (int ch = 0; ch < n_chunks; ++ch) {
       const int s = ch % kWStages, u = ch / kWStages;
       const int e0 = e_lo + ch * 32;
       const int nv = min(32, e_hi - e0);
       int32_t* mt = meta + (ch & 1) * 96;
       if (pt < 32) {
-        const bool ok = pt < nv;
-        mt[pt] = ok ? g.dst[e0 + pt] : -1;
-        mt[32 + pt] = ok ? g.src[e0 + pt] : 0;
-        mt[64 + pt] = ok ? g.rank[e0 + pt] : 0;
+        mt[pt] = nd, mt[32 + pt] = ns, mt[64 + pt] = nr;
+        const int e1 = e0 + 32;
+        const bool ok = ch + 1 < n_chunks && pt < min(32, e_hi - e1);
+        nd = ok ? g.dst[e1 + pt] : -1, ns = ok ? g.src[e1 + pt] : 0, nr = ok ? g.rank[e1 + pt] : 0;
       }
       asm volatile("bar.sync 1, %0;" ::"n"(kBProducers) : "memory");
       mbar_wait(&empty[s], (u + 1) & 1u);
@@ -480,8 +487,8 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArg
       }
       // B operand: hidden activations (32 edges x Hd), re-gathered like the forward
       uint8_t* bh = st + 2 * kWAPart;
-      // 4 slots = 12 gathered float4 in flight per thread (13 warps per CTA leave 128 registers per thread)
-#pragma unroll 4
+      // all 8 slots unrolled: up to 24 gathered float4 in flight per thread (13 warps per CTA leave 128 registers)
+#pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int idx = pt + kBProducers * j, r = idx >> 6, q = idx & 63;
         const int d = mt[r];
