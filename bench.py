@@ -307,13 +307,28 @@ def roofline(model, sb, tgt, train, step, args):
         peak, unit = pk["hbm"], "GB/s"
     traffic, traffic_src = ncu_traffic(name, args.workload)
     shares = {k: round(v["ms"] / total, 4) for k, v in sorted(rows.items(), key=lambda kv: -kv[1]["ms"])[:8]}
+
+    def one(key, r):
+        """A kernel of this library as a fraction of ITS roofline: tensor-bound kernels against the measured bf16
+        peak (their 3-pass schemes cap them at 1/3 (f16) or 1/6 (tf32) of it), HBM-bound ones against copy bandwidth."""
+        ms_l = r["ms"] / r["launches"]
+        if r["bound"] == "tensor" and r["flops"] > 0:
+            a = r["flops"] / r["launches"] / (ms_l * 1e-3) / 1e12
+            return {"kernel": key, "bound": "tensor", "achieved": round(a, 2), "unit": "TFLOP/s",
+                    "frac": round(a / pk["bf16_sustained"], 4), "share": round(r["ms"] / total, 4)}
+        if r["bytes"] > 0:
+            a = r["bytes"] / r["launches"] / (ms_l * 1e-3) / 1e9
+            return {"kernel": key, "bound": "hbm", "achieved": round(a, 1), "unit": "GB/s",
+                    "frac": round(a / pk["hbm"], 4), "share": round(r["ms"] / total, 4)}
+        return None
+    per_kernel = [x for x in (one(k, r) for k, r in sorted(rows.items(), key=lambda kv: -kv[1]["ms"])[:12]) if x]
     out = {"kernel": name, "bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
            "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
            "peak_source": pk["source"] + (" (bf16 dense, sustained)" if bound == "tensor" else " (copy bandwidth)"),
            "avg_launch_ms": round(avg_ms, 5), "launches_per_step": top["launches"] // n,
            "share_of_own_kernel_time": round(top["ms"] / total, 4),
            "own_kernels_ms_per_step": round(total / n, 4), "own_kernel_shares": shares,
-           "note": top.get("note", "")}
+           "per_kernel": per_kernel, "note": top.get("note", "")}
     if bound == "tensor":
         # fp32 parity needs three tensor passes per product (DESIGN.md section 3): kind::f16 passes (the bf16 rate)
         # for the f16x3 kernels, kind::tf32 passes (half that rate) for the others

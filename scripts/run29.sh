@@ -14,3 +14,7 @@ python scripts/ncu_metrics.py $O/${R}_cfg2_train_full_raw.csv $O/${R}_cfg2_train
 gzip -f $O/${R}_cfg2_train_full_raw.csv
 timeout 200 python scripts/profile_step.py cfg2_train > $O/${R}_cfg2_train_torch_profiler.txt 2>&1
 du -sh $O
+timeout 200 ncu --set full --clock-control none --import-source on -k 'regex:edge_wgrad' -c 1 -o /tmp/${R}_wgrad python scripts/ncu_layer.py cfg2_train 1 > $O/ncu_w.log 2>&1
+ncu -i /tmp/${R}_wgrad.ncu-rep --page source --csv --print-source sass > /tmp/wgrad_src.csv 2>/dev/null
+python scripts/sass_hot.py /tmp/wgrad_src.csv 0 45 > $O/${R}_edge_wgrad_sass_hot.txt 2>&1; head -2 $O/${R}_edge_wgrad_sass_hot.txt | cut -c1-120
+du -sh $O
