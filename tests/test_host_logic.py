@@ -124,3 +124,27 @@ def test_optimizer_step_invalidates_packed_operands():
         before = ops._pack_epoch
         torch.optim.AdamW(p, lr=1e-3, **kw).step()
         assert ops._pack_epoch > before, f"AdamW({kw}).step() did not invalidate the packed operands"
+
+
+@pytest.mark.parametrize("buckets", [(1, 1, 1), (7, 3, 5), (256, 128, 512)])
+def test_pad_batch_structure(buckets):
+    """pad_batch keeps the reference layout (source-sorted edges, K per atom, sorted segment vectors) for any bucket
+    size, including the case where the pair count already sits on a bucket boundary (no dummy pairs)."""
+    from cgat_b200 import batching
+    sb = synthetic.make_batch(9, 6, seed=11)
+    pb = batching.pad_batch(sb, buckets=buckets)
+    g, (w, fea, si, ni, ci) = pb.graph, pb.roost
+    n, nc, mc = g.x.shape[0], fea.shape[0], si.shape[0]
+    assert n % buckets[0] == 0 and nc % buckets[1] == 0 and mc % buckets[2] == 0
+    assert n > sb.graph.x.shape[0] and nc > sb.roost[1].shape[0] and mc >= sb.roost[2].shape[0]
+    K = 6
+    assert g.edge_index.shape == (2, n * K) and torch.equal(g.edge_index[0], torch.arange(n).repeat_interleave(K))
+    assert int(g.edge_attr.min()) >= 1 and int(g.edge_attr.max()) <= K
+    assert bool((g.batch[1:] >= g.batch[:-1]).all()) and int(g.batch[-1]) == sb.num_crystals == g.num_graphs - 1
+    assert bool((g.batch[g.edge_index[0]] == g.batch[g.edge_index[1]]).all()), "an edge crosses a crystal boundary"
+    assert bool((si[1:] >= si[:-1]).all()) and bool((ci[1:] >= ci[:-1]).all())
+    assert bool((ci[si] == ci[ni]).all()), "a Roost pair crosses a crystal boundary"
+    assert bool((w > 0).all()) and g.y.shape[0] == g.num_graphs and float(g.y[-1]) == 0.0
+    # the real part is untouched
+    n0 = sb.graph.x.shape[0]
+    assert torch.equal(g.x[:n0], sb.graph.x) and torch.equal(g.edge_index[:, : n0 * K], sb.graph.edge_index)
