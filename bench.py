@@ -167,7 +167,7 @@ def run_ours(args):
         if runner is None:
             sb = sb.to(dev, non_blocking=True)
         res = run(sb, targets[i % len(pool)])               # graph mode: pinned host -> the graph's static buffers
-        return float(res) if train else res[:, 0].cpu()     # device -> host read of the step's result
+        return float(res.detach()) if train else res[:, 0].cpu()     # device -> host read of the step's result
 
     def timed(fn, steps):
         if world > 1:
@@ -215,7 +215,7 @@ def run_ours(args):
             for p in model.parameters():
                 p.grad = None                                 # the graphs own their gradient buffers
         roof = roofline(model, dev_pool[0], targets[0], train, step, args)
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (the other ranks would idle)
         cpu = cpu_baseline(wl, net_kw, train)
     if world > 1:
         dist.barrier()
@@ -371,7 +371,7 @@ def oracle_step_fn(wl, net_kw, train, n_crystals):
             opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
-            return float(loss)
+            return float(loss.detach())
         with torch.no_grad():
             return O.cgat_forward(sd, cfg, sb.graph, sb.roost, as_written=True)
     return step

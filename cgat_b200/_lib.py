@@ -17,6 +17,8 @@ _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
 
+ABI_VERSION = 2  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
+
 # name -> (restype, argtypes); must list every symbol declared in include/cgat_b200.h
 SIGNATURES = {
     "cgat_abi_version": (ctypes.c_int, []),
@@ -82,6 +84,9 @@ def load():
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError if the symbol is not exported
         fn.restype, fn.argtypes = res, args
+    if lib.cgat_abi_version() != ABI_VERSION:
+        raise CgatLibraryError(f"{LIB_PATH} has ABI version {lib.cgat_abi_version()}, this package binds version "
+                               f"{ABI_VERSION}: rebuild with `python -m cgat_b200.build --force`")
     _lib = lib
     return lib
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CGAT_B200_ABI_VERSION 1
+#define CGAT_B200_ABI_VERSION 2 /* 2: cgat_edge_attn_bwd_prep gained bias_sums; f16 entry points */
 
 int cgat_abi_version(void);
 const char* cgat_last_error(void);
