@@ -73,3 +73,32 @@ def signature(sb: SyntheticBatch):
     """What a captured graph is keyed on: every size a kernel launch bakes in."""
     g = sb.graph
     return (g.x.shape[0], g.edge_index.shape[1], g.num_graphs, sb.roost[1].shape[0], sb.roost[2].shape[0])
+
+
+def collate_graphs(graphs) -> GraphBatch:
+    """What torch_geometric's `Batch.from_data_list` does for the attributes CGAtNet.forward reads (reference
+    CGAT/lightning_module.py:199-200, CGAT/data.py:139-144): concatenate x / edge_attr / y, shift every crystal's
+    edge_index by its node offset, and emit the sorted `batch` vector.  `graphs`: objects with x (n,D), edge_index
+    (2,e) int64, edge_attr (e,) int64 and optionally y."""
+    graphs = list(graphs)
+    sizes = torch.tensor([g.x.shape[0] for g in graphs], dtype=torch.int64)
+    offsets = torch.cumsum(sizes, 0) - sizes
+    x = torch.cat([g.x for g in graphs])
+    edge_index = torch.cat([g.edge_index + off for g, off in zip(graphs, offsets.tolist())], dim=1)
+    edge_attr = torch.cat([g.edge_attr for g in graphs])
+    batch = torch.repeat_interleave(torch.arange(len(graphs), dtype=torch.int64), sizes)
+    ys = [getattr(g, "y", None) for g in graphs]
+    y = None if any(v is None for v in ys) else torch.cat([v.reshape(-1) for v in ys])
+    return GraphBatch(x, edge_index, edge_attr, batch, y, num_graphs=len(graphs))
+
+
+def collate(samples) -> SyntheticBatch:
+    """Per-crystal samples -> one collated batch in the layout CGAtNet.forward takes.  `samples`: iterable of
+    (graph, (weights, fea, self_idx, nbr_idx)) as the reference's CompositionData.__getitem__ yields them
+    (CGAT/data.py:139-144); the Roost part goes through roost_message.collate_batch."""
+    from .roost_message import collate_batch
+    samples = list(samples)
+    graph = collate_graphs(g for g, _ in samples)
+    roost = collate_batch([r for _, r in samples])
+    n_atoms = np.array([g.x.shape[0] for g, _ in samples], dtype=np.int64)
+    return SyntheticBatch(graph, roost, n_atoms)
