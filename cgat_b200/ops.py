@@ -546,7 +546,8 @@ class _EdgeAttentionFused(torch.autograd.Function):
         signs = torch.empty(2 * heads * kcn * max(e, 1), dtype=torch.int32, device=dev)
         flops2 = 2.0 * e * heads * hd * 2 * f
         # per-CTA column sums of d_msg | d_gate (the second-layer bias gradients) come out of the same kernel
-        bsum = torch.empty((int(lib.cgat_edge_attn_grid(e)), 2, heads, f), dtype=torch.float32, device=dev)
+        bsum = (torch.empty if e > 0 else torch.zeros)((int(lib.cgat_edge_attn_grid(e)), 2, heads, f),
+                                                      dtype=torch.float32, device=dev)   # e == 0: no launch, no writes
         _lib.call("cgat_edge_attn_bwd_prep_f16" if ctx.f16 else "cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T),
                   _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed), _lib.ptr(b2a),
