@@ -125,7 +125,7 @@ def edge_attention_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2
 
 
 # ----------------------------------------------------------------------------------------------
-# Tensor-core pieces (tcgen05, 3xTF32 error-compensated; fp32 in / fp32 out)
+# Tensor-core pieces (tcgen05, three error-compensated passes per product — kind::tf32 or kind::f16; fp32 in / out)
 # ----------------------------------------------------------------------------------------------
 def gemm3x(a, w, bias=None, act=0, out=None):
     """act(a @ w.T + bias) on the tensor cores (cgat_gemm3x_nt). a (M,K), w (N,K): rows contiguous."""
@@ -487,11 +487,12 @@ def _first_layer_operands(w1a, w1m, b1a, b1m, f, fe):
 
 
 class _EdgeAttentionFused(torch.autograd.Function):
-    """Forward: per-atom / per-rank first-layer projections (cgat_gemm3x_nt) + the fused gather /
-    second-layer MMA / segmented-softmax kernel (cgat_edge_attn_fwd).  No per-edge tensor is written.
-    Backward: cgat_edge_attn_bwd_prep (per-edge dL/da, dL/dv + sign masks), two cgat_edge_attn_dgrad passes
-    (edges grouped by destination / by source), cgat_edge_attn_wgrad, and the first-layer products on
-    cgat_gemm3x_nt / cgat_gemm3x_tn.  Deterministic, atomic-free."""
+    """Forward: per-atom / per-rank first-layer projections (cgat_gemm3x_nt_res / cgat_gemm3x_nt) + the fused
+    gather / second-layer MMA / segmented-softmax kernel (cgat_edge_attn_fwd[_f16]).  No per-edge tensor is written.
+    Backward: cgat_edge_attn_bwd_prep[_f16] (per-edge dL/da, dL/dv, LeakyReLU sign masks and the second-layer bias
+    gradients), cgat_edge_attn_dgrad (per-edge dL/d pre-activation), cgat_edge_attn_reduce (its per-destination /
+    per-source / per-rank sums), cgat_edge_attn_wgrad, and the first-layer products on cgat_gemm3x_nt_splitk /
+    cgat_gemm3x_tn.  Deterministic, atomic-free."""
 
     @staticmethod
     def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads, f16):
