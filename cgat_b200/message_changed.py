@@ -14,6 +14,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import ops
+
 LEAKY_SLOPE = 0.01  # nn.LeakyReLU() default; the reference never passes its negative_slope argument
 
 
@@ -26,9 +28,13 @@ class SimpleNetwork(nn.Module):
         self.fc_out = nn.Linear(widths[-1], output_dim)
 
     def forward(self, fea):
+        if fea.dim() != 2:
+            for layer in self.fcs:
+                fea = F.leaky_relu(layer(fea), LEAKY_SLOPE)
+            return self.fc_out(fea)
         for layer in self.fcs:
-            fea = F.leaky_relu(layer(fea), LEAKY_SLOPE)
-        return self.fc_out(fea)
+            fea = ops.linear_act(fea, layer.weight, layer.bias, 1)
+        return ops.linear_act(fea, self.fc_out.weight, self.fc_out.bias, 0)
 
     def __repr__(self):
         return type(self).__name__
@@ -61,7 +67,7 @@ class ResidualNetwork(nn.Module):
 
     def forward(self, fea, *, last_layer=True):
         for i, (fc, skip) in enumerate(zip(self.fcs, self.res_fcs)):
-            branch = F.relu(fc(fea))
+            branch = ops.linear_act(fea, fc.weight, fc.bias, 3) if fea.dim() == 2 else F.relu(fc(fea))
             if self.if_rezero:
                 branch = self.rezeros[i](branch)
             fea = branch + skip(fea)

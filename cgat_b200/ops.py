@@ -84,6 +84,9 @@ _TRUNK = os.environ.get("CGAT_B200_TRUNK", "1") != "0"   # hypernetwork trunks: 
 _F16X3 = os.environ.get("CGAT_B200_F16X3", "1") != "0"
 _F16X3_EDGE = os.environ.get("CGAT_B200_F16X3_EDGE", "1") != "0"   # the same for the edge-attention forward / bwd_prep
 _EDGE_W2_PRESCALE = 64.0   # cgat_edge_attn_*_f16 expect W2 packed as f16(w * 2^6) hi/lo with an unscaled lo
+# EXPERIMENTAL, off by default (not yet measured on the GPU): the small MLPs around the fused kernels (Roost, crystal
+# pool, output network, edge table) on the 3-pass tensor-core GEMMs instead of the library's SIMT sgemm kernels
+_LINEAR3X = os.environ.get("CGAT_B200_LINEAR3X", "0") == "1"
 
 
 def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
@@ -141,6 +144,46 @@ def gemm3x(a, w, bias=None, act=0, out=None):
               out.data_ptr(), out.stride(0), M, N, K, act, _lib.stream(),
               work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))
     return out
+
+
+class _Linear3x(torch.autograd.Function):
+    """act(x @ w.T + b) with forward on cgat_gemm3x_nt (bias + activation in its epilogue) and backward on
+    cgat_gemm3x_nt (dL/dx) / cgat_gemm3x_tn (dL/dw).  act: 0 none, 1 LeakyReLU(0.01), 3 ReLU — both have
+    sign(out) == sign(pre-activation), so only the output is saved."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, act):
+        x, w = _f32c(x), weight.contiguous()
+        out = gemm3x(x, w, None if bias is None else bias.contiguous(), act)
+        ctx.act, ctx.has_bias = act, bias is not None
+        ctx.save_for_backward(x, w, out if act else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w, out = ctx.saved_tensors
+        g = _f32c(g)
+        if ctx.act == 1:
+            g = torch.where(out > 0, g, g * LEAKY_SLOPE)
+        elif ctx.act == 3:
+            g = g * (out > 0)
+        g_x = gemm3x(g, w.t().contiguous()) if ctx.needs_input_grad[0] else None     # (M,N) @ (N,K)
+        g_w = gemm3x_tn(g, x) if ctx.needs_input_grad[1] else None                    # g^T x: (N,K)
+        g_b = g.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return g_x, g_w, g_b, None
+
+
+def linear_act(x, weight, bias=None, act=0):
+    """act(x @ weight.T + bias) for a 2-D x; act: 0 none, 1 LeakyReLU(0.01), 3 ReLU.  The library path (cuBLAS fp32
+    via torch) unless CGAT_B200_LINEAR3X=1 selects the 3-pass tensor-core GEMMs."""
+    if _LINEAR3X and x.is_cuda and x.dim() == 2 and x.shape[1] % 4 == 0 and x.shape[0] > 0:
+        return _Linear3x.apply(x, weight, bias, act)
+    y = torch.nn.functional.linear(x, weight, bias)
+    if act == 1:
+        return torch.nn.functional.leaky_relu(y, LEAKY_SLOPE)
+    if act == 3:
+        return torch.relu(y)
+    return y
 
 
 def gemm3x_res(a, w_packed, n_out, bias=None, act=0):

@@ -3,7 +3,7 @@
 import pytest
 import torch
 
-from cgat_b200 import _lib
+from cgat_b200 import _lib, ops
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -104,3 +104,31 @@ def test_gemm3x_splitk_matches_fp64(M, N, K):
     rel = ((c.double() - ref).abs() / bound).max().item()
     limit = 3e-7 + 2e-7 * (3 * K / 8) ** 0.5
     assert rel <= limit, f"max err / sum|a||b| = {rel:.3e} (limit {limit:.3e})"
+
+
+@pytest.mark.skipif(__import__("os").environ.get("CGAT_B200_LINEAR3X") != "1",
+                    reason="experimental path: set CGAT_B200_LINEAR3X=1 (not yet validated on the GPU)")
+@pytest.mark.parametrize("M,N,K,act,bias", [(500, 1024, 640, 3, True), (4700, 256, 256, 1, True), (4700, 1, 256, 0, True),
+                                           (13, 128, 128, 1, True), (500, 512, 1024, 0, False), (1750, 127, 200, 0, True)])
+def test_linear3x_matches_fp64(M, N, K, act, bias):
+    """ops._Linear3x (forward cgat_gemm3x_nt with fused bias / activation, backward gemm3x_nt + gemm3x_tn) against
+    fp64 autograd, at the shapes of the Roost / pool / output MLPs."""
+    g = torch.Generator().manual_seed(M + N)
+    x = torch.randn(M, K, generator=g)
+    w = torch.randn(N, K, generator=g) / K ** 0.5
+    b = torch.randn(N, generator=g) * 0.1 if bias else None
+    gw = torch.randn(M, N, generator=g)
+    xd, wd = x.double().requires_grad_(True), w.double().requires_grad_(True)
+    bd = None if b is None else b.double().requires_grad_(True)
+    ref = torch.nn.functional.linear(xd, wd, bd)
+    ref = [ref, torch.nn.functional.leaky_relu(ref, 0.01), None, torch.relu(ref)][act]
+    (ref * gw.double()).sum().backward()
+    xc, wc = x.to(DEV).requires_grad_(True), w.to(DEV).requires_grad_(True)
+    bc = None if b is None else b.to(DEV).requires_grad_(True)
+    out = ops._Linear3x.apply(xc, wc, bc, act)
+    (out * gw.to(DEV)).sum().backward()
+    assert (out.detach().double().cpu() - ref.detach()).abs().max().item() < 2e-5
+    assert (xc.grad.double().cpu() - xd.grad).abs().max().item() < 1e-4
+    assert (wc.grad.double().cpu() - wd.grad).abs().max().item() < 1e-4 + 1e-5 * wd.grad.abs().max().item()
+    if bias:
+        assert (bc.grad.double().cpu() - bd.grad).abs().max().item() < 1e-4 + 1e-5 * bd.grad.abs().max().item()
