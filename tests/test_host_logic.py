@@ -166,3 +166,11 @@ def test_collate_round_trip():
     for a, b in zip(back.roost, sb.roost):
         assert torch.equal(a, b)
     assert back.graph.num_graphs == sb.num_crystals and np.array_equal(back.n_atoms, sb.n_atoms)
+
+
+def test_graphed_step_needs_a_capturable_optimizer():
+    """A non-capturable optimizer would bake its host-side step counter into the graph: refuse it up front."""
+    from cgat_b200 import graphed
+    lin = torch.nn.Linear(4, 4)
+    with pytest.raises(ValueError):
+        graphed.GraphedTrainStep(lin, torch.optim.AdamW(lin.parameters(), lr=1e-3), torch.nn.L1Loss())
