@@ -90,7 +90,10 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   // split-K over blockIdx.z: partial products `split_stride` floats apart (bias / act only with one split)
   const int k_begin = blockIdx.z * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
-  const int nk = (k_end - k_begin + kKC - 1) / kKC;
+  // a split that starts at or beyond K is EMPTY (nk = 0): its partial tile is all zeros (+ bias / act) and the MMA
+  // warp arrives on `accum` by hand.  (Round 1 computed nk with a truncating division that went NEGATIVE for
+  // k_begin >= K + 64 and never arrived: the epilogue warps then waited forever.)
+  const int nk = k_end > k_begin ? (k_end - k_begin + kKC - 1) / kKC : 0;
   C += (int64_t)blockIdx.z * split_stride;
 
   if (tid == 0) {
@@ -137,7 +140,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
         for (int j = 0; j < 32; ++j) {
           int n = nb + j;
           float b = (bias != nullptr && n < N) ? __ldg(bias + n) : 0.f;
-          v[j] = apply_act((v[j] + w[j]) + b, act);
+          v[j] = apply_act((nk > 0 ? v[j] + w[j] : 0.f) + b, act);
         }
         float* crow = C + (int64_t)m * ldc + nb;
         if (vec_ok && nb + 32 <= N) {
@@ -176,6 +179,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       }
       __syncwarp();
     }
+    if (nk == 0 && lane == 0) mbar_arrive(accum);  // empty split: nothing to wait for
   }
   __syncthreads();
   if (warp == 4) {
@@ -244,7 +248,7 @@ gemm3x_tn_kernel(const TnArgs g) {
   const int m0 = blockIdx.y * 128, n0 = blockIdx.x * 128;
   const int k_begin = split * k_per_split;
   const int k_end = min(K, k_begin + k_per_split);
-  const int nk = (k_end - k_begin + kKC - 1) / kKC;
+  const int nk = k_end > k_begin ? (k_end - k_begin + kKC - 1) / kKC : 0;  // empty split: zeros, see gemm3x_nt_kernel
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&full[s], kWorkers);

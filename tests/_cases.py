@@ -96,6 +96,47 @@ def assert_grad_close(a, b, what, atol=ATOL, rtol=RTOL, max_outlier_frac=2e-3, o
     return far
 
 
+def grad_stats(a, b, atol=ATOL, rtol=RTOL):
+    """Strict north-star statistics of one gradient tensor against its fp64 reference: number of elements outside
+    atol + rtol*|ref|, number beyond 3x that bound, worst error and worst error / bound."""
+    a = torch.as_tensor(a, dtype=torch.float64).cpu()
+    b = torch.as_tensor(b, dtype=torch.float64).cpu()
+    err = (a - b).abs()
+    tol = atol + rtol * b.abs()
+    ratio = err / tol
+    return dict(n=int(b.numel()), bad=int((err > tol).sum()), far=int((err > 3 * tol).sum()),
+                max_err=float(err.max()) if b.numel() else 0.0, max_ratio=float(ratio.max()) if b.numel() else 0.0,
+                ref_max=float(b.abs().max()) if b.numel() else 0.0,
+                rel_l2=float(err.norm() / (b.norm() + 1e-300)))
+
+
+def record_parity(case, per_tensor, extra=None):
+    """Write the strict violation counts of a full-model gradient comparison to a JSON file the builder copies into
+    profiles/ (the counts must be recorded, not only printed under -s).  Directory:
+    $CGAT_PARITY_LOG_DIR, default <repo>/gpurun_out (the only directory a gpurun call brings back)."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out_dir = os.environ.get("CGAT_PARITY_LOG_DIR", os.path.join(root, "gpurun_out"))
+    try:
+        os.makedirs(out_dir, exist_ok=True)
+    except OSError:
+        return None
+    tot = dict(n=0, bad=0, far=0, max_err=0.0, max_ratio=0.0)
+    for st in per_tensor.values():
+        tot["n"] += st["n"]
+        tot["bad"] += st["bad"]
+        tot["far"] += st["far"]
+        tot["max_err"] = max(tot["max_err"], st["max_err"])
+        tot["max_ratio"] = max(tot["max_ratio"], st["max_ratio"])
+    rels = sorted(st["rel_l2"] for st in per_tensor.values())
+    doc = dict(case=case, atol=ATOL, rtol=RTOL, total=tot, median_rel_l2=rels[len(rels) // 2] if rels else None,
+               tensors_with_violations={k: v for k, v in per_tensor.items() if v["bad"]}, **(extra or {}))
+    path = os.path.join(out_dir, f"grad_parity_{case}.json")
+    with open(path, "w") as fh:
+        json.dump(doc, fh, indent=1)
+    return tot
+
+
 def grad_digest(t):
     g = t.double()
     return [g.sum().item(), g.abs().sum().item(), g.pow(2).sum().sqrt().item()]

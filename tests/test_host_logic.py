@@ -174,3 +174,22 @@ def test_graphed_step_needs_a_capturable_optimizer():
     lin = torch.nn.Linear(4, 4)
     with pytest.raises(ValueError):
         graphed.GraphedTrainStep(lin, torch.optim.AdamW(lin.parameters(), lr=1e-3), torch.nn.L1Loss())
+
+
+def test_split_planner_never_emits_an_empty_split():
+    """ops.plan_split (used by every split-K launch: gemm3x_splitk, gemm3x_tn, gemm3x_tn_batched): for every
+    contraction length up to 70 000 and every split count the planners can ask for, no part starts at or beyond
+    K.  Round 1 hung on such parts (VERDICT r01 weak #1: K = 5376 with 18 parts -> the 18th starts at 5440)."""
+    from cgat_b200.ops import plan_split
+    wants = (1, 2, 3, 4, 5, 7, 9, 10, 16, 18, 20, 37, 74, 148, 296)
+    for k in range(1, 70001):
+        for want in wants:
+            n = plan_split(k, want)
+            k_per = -(-(-(-k // n)) // 32) * 32           # what cgat_gemm3x_tn / launch_gemm compute from n
+            assert 1 <= n <= want
+            assert (n - 1) * k_per < k, (k, want, n, k_per)
+    # the planners' own requests at the sizes that hung: trunk weight gradients, batch 16 -> 18 parts wanted
+    for k in (4609, 5185, 5376, 5377, 5888, 6400):
+        want = max(1, min((k + 255) // 256, (2 * 148) // 16))
+        n = plan_split(k, want)
+        assert (n - 1) * (-(-(-(-k // n)) // 32) * 32) < k
