@@ -134,10 +134,11 @@ def run_ours(args):
     dev_pool = [sb.to(dev) for sb in pool]
     pin_pool = [sb.pin_memory() for sb in pool]
     targets = [target_norm(sb, dev, wl["crystals"]) for sb in pool]
-    sync = cdist.GradSync(model, world) if train else None
-    opt = torch.optim.AdamW([p for p in model.parameters()], lr=LR, weight_decay=WD, fused=True,
-                            capturable=use_graph) if train else None
-    crit = torch.nn.L1Loss()
+    from cgat_b200 import optim as coptim
+    # AdamW over flat buffers + bucketed, backward-overlapped gradient all-reduce (cgat_b200/optim.py, distributed.py)
+    opt = coptim.FlatAdamW(model, lr=LR, weight_decay=WD, world_size=world) if train else None
+    sync = opt.sync if train else None
+    crit = coptim.l1_loss                                    # reference lightning_module.py:237-240 (nn.L1Loss)
     n_real = wl["crystals"]
 
     def step(sb, tgt):
@@ -146,7 +147,7 @@ def run_ours(args):
             out = model(sb.graph, sb.roost)
             loss = crit(out[:n_real, :1], tgt[:n_real])      # reference lightning_module.py:237-240
             loss.backward()
-            sync.all_reduce()
+            sync.finish()
             opt.step()
             sync.zero_grad()
             return loss
@@ -155,7 +156,8 @@ def run_ours(args):
 
     runner = None
     if use_graph:
-        runner = graphed.GraphedTrainStep(model, opt, crit, sync) if train else graphed.GraphedForward(model)
+        runner = (graphed.GraphedTrainStep(model, opt, crit, sync, graph_collectives=not args.no_graph_collectives)
+                  if train else graphed.GraphedForward(model))
 
     def run(sb, tgt):
         if runner is None:
@@ -211,10 +213,14 @@ def run_ours(args):
     roof = cpu = None
     if rank == 0 or (train and world > 1):
         # the profiled steps contain the gradient all-reduce, so on several ranks every rank runs them (rank 0 reports)
-        if runner is not None and train:
+        if train:
+            sync.zero_grad()
             for p in model.parameters():
                 p.grad = None                                 # the graphs own their gradient buffers
         roof = roofline(model, dev_pool[0], targets[0], train, step, args)
+    fwd = None
+    if train and not args.no_forward_record and not wl["net"] and wl["max_nbr"] == WORKLOADS["cfg3_infer"]["max_nbr"]:
+        fwd = forward_record(model, rank, world, dev, args, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (the other ranks would idle)
         cpu = cpu_baseline(wl, net_kw, train)
     if world > 1:
@@ -228,14 +234,15 @@ def run_ours(args):
         graph_cfg = {"captures": runner.captures, "buckets_atoms_elems_pairs": list(batching.DEFAULT_BUCKETS),
                      "padded_atoms": int(sum(sb.graph.x.shape[0] for sb in pool) / len(pool)),
                      "note": "one whole-step graph per shape bucket (forward, loss, backward, AdamW; on >1 rank the NCCL "
-                             "all-reduce and AdamW follow the graph eagerly); "
+                             "all-reduces are captured too, one per gradient bucket, overlapping backward); "
                              "batches padded with one dummy crystal; throughput counts real crystals only"}
     line = {
         "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),
         "value": round(value, 2), "unit": "crystals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.workload}: CGAtNet default hyper-parameters "
+        "config": {"workload": args.workload,
+                   "description": f"CGAtNet default hyper-parameters "
                                f"(F={net_kw['elem_fea_len']}, heads={net_kw['msg_heads']}, layers={net_kw['n_graph']}, "
                                f"vector attention, edge updates, ReZero, concat pooling), {wl['crystals']} synthetic "
                                f"crystals per GPU per step, {wl['max_nbr']} neighbours, ~{n_atoms} atoms / "
@@ -252,7 +259,31 @@ def run_ours(args):
         "roofline": roof,
         "cpu_baseline": cpu,
     }
+    if fwd is not None:
+        line["forward"] = fwd   # BASELINE.json's metric is "fwd & train step": the forward half, same process, same N
     print(json.dumps(line))
+
+
+def forward_record(model, rank, world, dev, args, timed):
+    """cfg3 (BASELINE.json configs[2]): screening inference, no_grad, 5000-crystal batches per GPU (reference
+    CGAT/predict.py:20), sharded over the ranks with no collective — measured in the same process with the weights the
+    train steps left behind, so that the driver's run at every N carries the forward number too."""
+    from cgat_b200 import batching, graphed
+    wl = WORKLOADS["cfg3_infer"]
+    pool = [batching.pad_batch(sb) for sb in make_pool(wl, rank, 2)]
+    dev_pool, pin_pool = [sb.to(dev) for sb in pool], [sb.pin_memory() for sb in pool]
+    runner = graphed.GraphedForward(model)
+    steps = max(3, min(args.steps, 10))
+    for i in range(len(pool) + 1 + 3):
+        runner(dev_pool[i % len(pool)])
+    ms = timed(lambda i: runner(dev_pool[i % len(pool)]), steps)
+    ms_e2e = timed(lambda i: runner(pin_pool[i % len(pool)])[:, 0].cpu(), steps)
+    crystals = wl["crystals"] * world
+    return {"metric": "crystals/sec forward (no_grad)", "workload": "cfg3_infer", "value": round(crystals * steps / (ms / 1e3), 2),
+            "unit": "crystals/s", "ms_per_step": round(ms / steps, 4), "steps": steps, "crystals_per_gpu": wl["crystals"],
+            "scaling": "weak", "parallelism": f"shard{world} (no collective)",
+            "e2e": {"value": round(crystals * steps / (ms_e2e / 1e3), 2), "unit": "crystals/s",
+                    "h2d_bytes_per_step": pool[0].nbytes(), "d2h_bytes_per_step": wl["crystals"] * 4}}
 
 
 KERNEL_NAMES = {  # profile key (ops.py `work`) -> kernel names in the ncu capture (profiles/*_kernel_metrics.json)
@@ -377,25 +408,67 @@ def oracle_step_fn(wl, net_kw, train, n_crystals):
     return step
 
 
+REF_SAMPLE = 32   # crystals per CPU step: a 500-crystal step of the unmodified modules needs ~30 GB and ~1 min on 16 cores
+
+
+def reference_step_fn(wl, net_kw, train, n_crystals):
+    """One step of the reference's CPU path on `n_crystals` crystals of the workload -> (step(i), kind).
+    kind "reference": the UNMODIFIED reference modules from oracle/_ref/cgat_reference.zip (oracle/build_ref.py packs
+    them where /root/reference exists; stand-ins only for torch_scatter / torch_geometric) driven like
+    lightning_module.py:206-240 + AdamW.  kind "port": the oracle restatement, if the archive is missing."""
+    from oracle import build_ref
+    ref = build_ref.import_ref()
+    if ref is None:
+        return oracle_step_fn(wl, net_kw, train, n_crystals), "port"
+    from cgat_b200 import synthetic, weights
+    from oracle import standins
+    torch.set_num_threads(os.cpu_count())
+    torch.manual_seed(0)
+    model = weights.load_seeded(ref["CGAT"].CGAtNet(200, **net_kw), 0)
+    lo, hi = wl["atoms"]
+    pool = []
+    for i in range(2):
+        sb = synthetic.make_batch(n_crystals, wl["max_nbr"], seed=1 + i, atoms_lo=lo, atoms_hi=hi)
+        b = standins.Batch(x=sb.graph.x, edge_index=sb.graph.edge_index, edge_attr=sb.graph.edge_attr, y=sb.graph.y)
+        b.batch = sb.graph.batch
+        y = sb.graph.y
+        pool.append((b, sb.roost, ((y - y.mean()) / (y.std() + 1e-6)).view(-1, 1)))
+    opt = torch.optim.AdamW(model.parameters(), lr=LR, weight_decay=WD) if train else None
+    crit = torch.nn.L1Loss()
+
+    def step(i):
+        b, roost, tgt = pool[i % 2]
+        if train:
+            out = model(b, (t for t in roost))                # reference lightning_module.py:198-206
+            loss = crit(out[:, :1], tgt)                       # :237-240
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            return float(loss.detach())
+        with torch.no_grad():
+            return model(b, (t for t in roost))
+    return step, "reference"
+
+
 def cpu_baseline(wl, net_kw, train):
-    """The reference's CPU path (oracle port of the unmodified modules, dead Edge attention included,
-    'as written') on this box's host cores, on a bounded sample of the same workload."""
-    n = min(64, wl["crystals"])  # the reference's default --batch-size
-    step = oracle_step_fn(wl, net_kw, train, n)
+    """The reference's CPU path on this box's host cores, on a bounded sample of the same workload."""
+    n = min(REF_SAMPLE, wl["crystals"])
+    step, kind = reference_step_fn(wl, net_kw, train, n)
     step(0)
     best = 1e30
-    for i in range(2):
+    for i in range(3):
         t = time.perf_counter()
         step(i + 1)
         best = min(best, time.perf_counter() - t)
-    return {"value": round(n / best, 3), "unit": "crystals/s", "cores": os.cpu_count(), "kind": "port",
-            "sample": f"{n} crystals per step ({'fwd+bwd+AdamW' if train else 'forward'}), best of 2 after 1 warm-up, "
-                      "oracle port of the reference modules incl. its dead Edge attention"}
+    return {"value": round(n / best, 3), "unit": "crystals/s", "cores": os.cpu_count(), "kind": kind,
+            "sample": f"{n} crystals per step ({'fwd+bwd+AdamW' if train else 'forward'}), best of 3 after 1 warm-up, "
+                      + ("unmodified reference modules (oracle/_ref) incl. their dead Edge attention"
+                         if kind == "reference" else "oracle port of the reference modules incl. its dead Edge attention")}
 
 
 def run_reference(args):
-    """--impl reference: the reference's own CPU implementation of the path (oracle port: the reference
-    is pure Python needing torch_geometric/torch_scatter, which are not installable here) on the host cores."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores (all threads): the
+    unmodified modules from oracle/_ref when that archive was built (where /root/reference exists), else the oracle port."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -404,8 +477,8 @@ def run_reference(args):
     kw.update(wl["net"])
     kw["neighbor_number"] = wl["max_nbr"]
     train = wl["train"]
-    n = min(64, wl["crystals"])
-    step = oracle_step_fn(wl, kw, train, n)
+    n = min(REF_SAMPLE, wl["crystals"])
+    step, kind = reference_step_fn(wl, kw, train, n)
     for i in range(args.warmup):
         step(i)
     t = time.perf_counter()
@@ -413,8 +486,10 @@ def run_reference(args):
         step(i)
     dt = time.perf_counter() - t
     value = n * args.steps / dt
-    sample = (f"{n} crystals per step (the reference's default batch size) of the {args.workload} workload, "
-              f"{'fwd+bwd+AdamW' if train else 'forward'} on CPU")
+    sample = (f"{n} crystals per step of the {args.workload} workload ({wl['crystals']} crystals per step on the GPU arm: "
+              f"a CPU step of that size needs ~30 GB and ~1 min, so the sample is bounded), "
+              f"{'fwd+bwd+AdamW' if train else 'forward'} on CPU, "
+              + ("unmodified reference modules" if kind == "reference" else "oracle port"))
     print(json.dumps({
         "impl": "reference",
         "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),
@@ -422,7 +497,7 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "sample": sample},
-        "cpu_baseline": {"value": round(value, 3), "unit": "crystals/s", "cores": os.cpu_count(), "kind": "port",
+        "cpu_baseline": {"value": round(value, 3), "unit": "crystals/s", "cores": os.cpu_count(), "kind": kind,
                          "sample": sample},
         "e2e": {"value": round(value, 3), "unit": "crystals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -436,6 +511,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_train", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph-collectives", action="store_true", help="several ranks: keep the NCCL all-reduce and "
+                    "the optimizer outside the captured graph (one blocking all-reduce after backward)")
+    ap.add_argument("--no-forward-record", action="store_true", help="skip the cfg3 forward sub-record")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "one captured CUDA graph per shape bucket")
     args = ap.parse_args()

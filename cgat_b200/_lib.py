@@ -19,7 +19,7 @@ _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
 
-ABI_VERSION = 2  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
+ABI_VERSION = 3  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
 
 # name -> (restype, argtypes); must list every symbol declared in include/cgat_b200.h
 SIGNATURES = {
@@ -66,6 +66,9 @@ SIGNATURES = {
     "cgat_edge_attn_reduce": (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I32, _I64, _I32, _P]),
     "cgat_edge_attn_wgrad_splits": (_I32, [_I32]),
     "cgat_edge_attn_wgrad": (ctypes.c_int, [_P] * 8 + [_I64, _I32, _I32, _I32, _P]),
+    "cgat_sum_parts": (ctypes.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P]),
+    "cgat_adamw_flat": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F32, _F32, _F32, _F32, _F32, _P]),
+    "cgat_l1_loss": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I32, _P]),
 }
 
 

@@ -52,11 +52,16 @@ class GraphedTrainStep:
     all-reduce is captured with the rest).  The first `eager_steps` calls run eagerly (lazy library initialisation,
     optimizer state), later calls capture on the first use of a bucket and replay afterwards."""
 
-    def __init__(self, model, optimizer, loss_fn, sync=None, eager_steps=1):
+    def __init__(self, model, optimizer, loss_fn, sync=None, eager_steps=1, graph_collectives=True):
         for grp in optimizer.param_groups:
             if not grp.get("capturable", False):
                 raise ValueError("GraphedTrainStep needs an optimizer created with capturable=True")
-        self.model, self.opt, self.loss_fn, self.sync = model, optimizer, loss_fn, sync
+        self.model, self.opt, self.loss_fn = model, optimizer, loss_fn
+        self.sync = sync if sync is not None else getattr(optimizer, "sync", None)
+        # several ranks: True = the bucketed NCCL all-reduces (launched from autograd hooks, overlapping backward) and
+        # the optimizer are captured with the rest; False = round-1 behaviour, the graph ends after the gradients are
+        # packed and one blocking all-reduce + the optimizer follow eagerly after every replay
+        self.graph_collectives = graph_collectives
         self.eager_left = max(1, int(eager_steps))
         self.slots = {}
         self.pool = None
@@ -67,18 +72,29 @@ class GraphedTrainStep:
     def _multi(self):
         return self.sync is not None and self.sync.world > 1
 
+    def _split(self):
+        """Several ranks with the collectives kept out of the graph."""
+        return self._multi() and not self.graph_collectives
+
     def _fwd_bwd(self, sb, target):
         out = self.model(sb.graph, sb.roost)
         n_real = sb.graph.num_graphs - 1
         loss = self.loss_fn(out[:n_real, :1], target[:n_real])
-        loss.backward()
-        if self._multi():
+        if self._split():
+            world, self.sync.world = self.sync.world, 1      # hooks copy the buckets but do not start collectives
+            loss.backward()
             self.sync.pack()             # live gradients -> the flat all-reduce buffer; p.grad = views into it
+            self.sync.world = world
+        else:
+            loss.backward()              # hooks pack each finished bucket and start its all-reduce at once
         return out, loss
 
     def _finish(self):
-        if self._multi():
-            self.sync.reduce()
+        if self.sync is not None:
+            if self._split():
+                self.sync.reduce()
+            else:
+                self.sync.finish()       # wait for the bucket all-reduces; a no-op copy flush on one rank
         self.opt.step()
 
     def _body(self, sb, target):
@@ -108,8 +124,8 @@ class GraphedTrainStep:
         slot.target.copy_(target, non_blocking=True)
         slot.graph.replay()
         self.replayed_launches += slot.launches
-        if self._multi():
-            self._finish()               # NCCL all-reduce + AdamW stay outside the graph on more than one rank
+        if self._split():
+            self._finish()               # NCCL all-reduce + optimizer outside the graph
         ops.invalidate_packed()          # the step changed the weights behind Python's back
         return slot.loss
 
@@ -126,9 +142,9 @@ class GraphedTrainStep:
         # from invalidating the capture (launches from the autograd thread into the capturing stream are still recorded)
         mode = "thread_local" if self._multi() else "global"
         with torch.cuda.graph(slot.graph, pool=self.pool, capture_error_mode=mode):
-            # one rank: the whole step; several ranks: forward + backward + gradient packing (the all-reduce and the
-            # optimizer follow eagerly after each replay, reading p.grad = views of the flat buffer)
-            out, loss = self._fwd_bwd(slot.inputs, slot.target) if self._multi() else self._body(slot.inputs, slot.target)
+            # the whole step (several ranks: incl. the bucketed NCCL all-reduces, which overlap backward as parallel
+            # branches of the graph); with graph_collectives=False: forward + backward + gradient packing only
+            out, loss = self._fwd_bwd(slot.inputs, slot.target) if self._split() else self._body(slot.inputs, slot.target)
             slot.out, slot.loss = out.detach(), loss.detach()
         slot.launches = _lib.launch_count() - before
         if self.pool is None:
@@ -145,16 +161,22 @@ class GraphedForward:
 
     def __init__(self, model, eager_calls=1):
         self.model = model
-        self.eager_left = max(1, int(eager_calls))
+        self.eager_calls = max(1, int(eager_calls))
+        self.eager_left = self.eager_calls
         self.slots = {}
         self.pool = None
         self.replayed_launches = 0
         self.captures = 0
+        self.epoch = ops._pack_epoch
 
     @torch.no_grad()
     def __call__(self, sb):
         dev = next(self.model.parameters()).device
         n_real = sb.graph.num_graphs - 1
+        if ops._pack_epoch != self.epoch:
+            # the weights changed since the graphs were captured (an optimizer step or a training-graph replay): the
+            # captured launches read packed operand images that have been replaced — drop them and start over
+            self.slots, self.eager_left, self.epoch = {}, self.eager_calls, ops._pack_epoch
         if self.eager_left > 0:
             self.eager_left -= 1
             d = sb.to(dev, non_blocking=True)

@@ -94,6 +94,13 @@ def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
     (reference MultiHeadNetwork.forward, CGAT/CGAT.py:103-109)."""
     n = fea.shape[0]
     out_dim, hd = w_out.shape[1], w_out.shape[2]
+    if _LINEAR3X and fea.is_cuda and n > 0 and fea.shape[1] % 4 == 0 and hd % 4 == 0 and out_dim % 4 == 0:
+        # own 3-pass tensor-core GEMMs: one wide first layer (bias + LeakyReLU in its epilogue), then one GEMM per
+        # head on that head's column block of the hidden activations (row-strided operand, no copy)
+        hid = linear_act(fea, w_in, b_in, 1)                                                  # (n, H*Hd)
+        outs = [_Linear3x.apply(hid[:, h * hd:(h + 1) * hd], w_out[h], b_out[h * out_dim:(h + 1) * out_dim], 0)
+                for h in range(heads)]
+        return torch.stack(outs, dim=1)                                                       # (n, H, Out)
     hid = torch.nn.functional.leaky_relu(torch.addmm(b_in, fea, w_in.t()), LEAKY_SLOPE)      # (n, H*Hd)
     hid = hid.view(n, heads, hd).transpose(0, 1)                                              # (H, n, Hd)
     out = torch.baddbmm(b_out.view(heads, 1, out_dim), hid, w_out.transpose(1, 2))            # (H, n, Out)
@@ -153,7 +160,11 @@ class _Linear3x(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias, act):
-        x, w = _f32c(x), weight.contiguous()
+        if x.dtype != torch.float32:
+            raise TypeError("cgat_b200 kernels are fp32")
+        if x.stride(1) != 1 or x.stride(0) % 4 or x.data_ptr() % 16:
+            x = x.contiguous()             # row-strided column blocks of a wider matrix are taken as they are
+        w = weight.contiguous()
         out = gemm3x(x, w, None if bias is None else bias.contiguous(), act)
         ctx.act, ctx.has_bias = act, bias is not None
         ctx.save_for_backward(x, w, out if act else None)
@@ -176,7 +187,10 @@ class _Linear3x(torch.autograd.Function):
 def linear_act(x, weight, bias=None, act=0):
     """act(x @ weight.T + bias) for a 2-D x; act: 0 none, 1 LeakyReLU(0.01), 3 ReLU.  The library path (cuBLAS fp32
     via torch) unless CGAT_B200_LINEAR3X=1 selects the 3-pass tensor-core GEMMs."""
-    if _LINEAR3X and x.is_cuda and x.dim() == 2 and x.shape[1] % 4 == 0 and x.shape[0] > 0:
+    # both contractions of the layer (over K forward, over N_out in dL/dx) need a multiple of 4: the 127-wide Roost
+    # embedding and the 1- / 2-wide output heads stay on the library
+    if (_LINEAR3X and x.is_cuda and x.dim() == 2 and x.shape[1] % 4 == 0 and weight.shape[0] % 4 == 0
+            and x.shape[0] > 0):
         return _Linear3x.apply(x, weight, bias, act)
     y = torch.nn.functional.linear(x, weight, bias)
     if act == 1:
@@ -197,6 +211,25 @@ def gemm3x_res(a, w_packed, n_out, bias=None, act=0):
               n_out, M, n_out, K, act, _lib.stream(),
               work=dict(key="gemm3x_nt_res", bound="tensor", flops=2.0 * M * n_out * K,
                         bytes=4.0 * (M * K + M * n_out)))
+    return out
+
+
+def sum_parts(parts, out=None, accumulate=False):
+    """out = [out +] parts.sum(dim=0) with this library's fixed-order reduction kernel (cgat_sum_parts): parts is a
+    contiguous (n_parts, ...) stack of split-K / split-atom partial results.  Replaces torch.sum at every such
+    place (176 library `reduce_kernel` launches per cfg2 step in round 1, profiles/r01n_*_launches_summary.txt)."""
+    n_parts = parts.shape[0]
+    if out is None:
+        if n_parts == 1:
+            return parts[0]
+        out = torch.empty(parts.shape[1:], dtype=torch.float32, device=parts.device)
+    n = out.numel()
+    if n == 0 or n_parts == 0:
+        return out if accumulate else out.zero_()
+    if not parts.is_contiguous() or not out.is_contiguous():
+        raise ValueError("sum_parts needs contiguous buffers")
+    _lib.call("cgat_sum_parts", _lib.ptr(parts), n_parts, n, _lib.ptr(out), n, int(accumulate), _lib.stream(),
+              work=dict(key="sum_parts", bound="hbm", bytes=4.0 * n * (n_parts + 1 + int(accumulate))))
     return out
 
 
@@ -227,7 +260,7 @@ def gemm3x_splitk(a, w, n_split=None):
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_nt_splitk", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), part.data_ptr(), N, M * N,
               M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))
-    return part[0] if n_split == 1 else part.sum(dim=0)
+    return sum_parts(part)
 
 
 def gemm3x_tn(a, b, n_split=None):
@@ -244,7 +277,7 @@ def gemm3x_tn(a, b, n_split=None):
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_tn", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), part.data_ptr(), N, M * N,
               M, N, K, n_split, _lib.stream(), work=dict(key="gemm3x_tn", bound="tensor", flops=2.0 * M * N * K))
-    return part[0] if n_split == 1 else part.sum(dim=0)
+    return sum_parts(part)
 
 
 # Packed operand caches are keyed on (the weight's autograd version, this epoch).  The version counter alone is
@@ -345,12 +378,12 @@ class _HyperLinear(torch.autograd.Function):
         buf = torch.empty((parts, n, f), dtype=torch.float32, device=y.device)
         _lib.call(rowscale, _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed), _lib.ptr(buf),
                   n, f, _lib.stream(), work=work)
-        g_y = buf.sum(dim=0)
+        g_y = sum_parts(buf)
         # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ the bias-tail rows unless they went through `e`)
         buf2 = torch.empty_like(buf)
         _lib.call(rowscale, _lib.ptr(y), _lib.ptr(g), None, _lib.ptr(w_packed_bt), _lib.ptr(buf2), n, f,
                   _lib.stream(), work=work)
-        g_z = buf2.sum(dim=0)
+        g_z = sum_parts(buf2)
         if not ctx.has_e:
             g_z = g_z + gemm3x(g, weight[ff:].t().contiguous())
         # weight gradient: dW[o*F+i,k] = sum_n g[n,o] y[n,i] z[n,k] — contraction over atoms, outer product on the fly
@@ -361,10 +394,7 @@ class _HyperLinear(torch.autograd.Function):
                   work=dict(key="hyper_wgrad", bound="tensor", flops=2.0 * n * f * ff,
                             note="3xTF32: 3 tensor passes per algorithmic flop"))
         g_w = torch.empty_like(weight)
-        if splits == 1:
-            g_w[:ff] = wpart[0]
-        else:
-            torch.sum(wpart, dim=0, out=g_w[:ff])
+        sum_parts(wpart, out=g_w[:ff])
         yz = torch.cat([y, z], dim=1)                      # bias-shaped rows: g^T [y | z]
         gyz = gemm3x_tn(g, yz)                             # (F, 2F), split over atoms to fill the SMs
         g_w[ff:] = gyz[:, f:]
@@ -408,9 +438,7 @@ def gemm3x_tn_batched(a_list, b_list, colsum=True):
     _lib.call("cgat_gemm3x_tn_batched", _lib.ptr_array(a_list), _lib.ptr_array(b_list), batch, a_list[0].stride(0),
               b_list[0].stride(0), _lib.ptr(part), _lib.ptr(csum), M, N, K, n_split, _lib.stream(),
               work=dict(key="gemm3x_tn_batched", bound="tensor", flops=2.0 * batch * M * N * K))
-    if n_split == 1:
-        return part[0], (csum[0] if colsum else None)
-    return part.sum(dim=0), (csum.sum(dim=0) if colsum else None)
+    return sum_parts(part), (sum_parts(csum) if colsum else None)
 
 
 def _trunk_packed(weights, transpose):
@@ -474,7 +502,7 @@ class _HyperTrunk(torch.autograd.Function):
                   _lib.ptr(D), _lib.ptr(dH), n, f, n_j, _lib.stream(),
                   work=dict(key="hyper_trunk_bwd", bound="tensor", flops=2.0 * n * f * f * _TRUNK_STEPS * n_j,
                             note="3xTF32 chain of 5 GEMMs per hyper-layer, activation tile resident on the SM"))
-        g_h = dH[0] if n_j == 1 else dH.sum(dim=0)
+        g_h = sum_parts(dH)
         # weight / bias gradients of the 4 tanh layers of every trunk in one launch: dW_s = D_s^T (input of layer s)
         a_list = [D[j, s] for j in range(n_j) for s in range(4)]
         b_list = [h if s == 0 else T[j, s - 1] for j in range(n_j) for s in range(4)]
@@ -638,16 +666,16 @@ class _EdgeAttentionFused(torch.autograd.Function):
                             bytes=4.0 * (2 * e * 2 * hhd + n * 4 * hhd + chunks * n_ranks * 2 * hhd),
                             note="reads d_pre twice (by destination, by source), writes dL/dP + per-rank partials"))
         del d_pre
-        d_t = d_rank.sum(dim=0)                                                     # (K+1, 2*HHd)
+        d_t = sum_parts(d_rank)                                                     # (K+1, 2*HHd)
         # 3. second-layer weight / bias gradients
         splits = int(lib.cgat_edge_attn_wgrad_splits(heads))
         part = torch.empty((splits, 2, heads, f, hd), dtype=torch.float32, device=dev)
         _lib.call("cgat_edge_attn_wgrad", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
                   _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(part), e, heads, f, hd, st,
                   work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2))
-        d_w2 = part.sum(dim=0)
+        d_w2 = sum_parts(part)
         g_w2a, g_w2m = d_w2[0].reshape(w2a.shape), d_w2[1].reshape(w2m.shape)
-        g_b2 = bsum.sum(dim=0)
+        g_b2 = sum_parts(bsum)
         g_b2m, g_b2a = g_b2[0].reshape(-1), g_b2[1].reshape(-1)
         # 4. first layer: P = x w_atom^T, T = tab w_rank^T + b1
         g_x = gemm3x_splitk(d_p, w_atom_t)

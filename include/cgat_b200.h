@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CGAT_B200_ABI_VERSION 2 /* 2: cgat_edge_attn_bwd_prep gained bias_sums; f16 entry points */
+#define CGAT_B200_ABI_VERSION 3 /* 2: cgat_edge_attn_bwd_prep gained bias_sums; f16 entry points. 3: train-step glue */
 
 int cgat_abi_version(void);
 const char* cgat_last_error(void);
@@ -245,6 +245,25 @@ int32_t cgat_edge_attn_wgrad_splits(int32_t heads);
 int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
                          const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
                          int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream);
+
+/* ---- train-step glue ----------------------------------------------------------
+ * cgat_sum_parts: out[i] = (accumulate ? out[i] : 0) + sum_{p < n_parts} parts[p * part_stride + i], parts added in
+ *   index order (deterministic).  Sums the split-K / split-atom partial results of the kernels above (replaces the
+ *   library reductions autograd would run at the same places).
+ * cgat_adamw_flat: one AdamW step (decoupled weight decay, torch.optim.AdamW arithmetic) over flat parameter /
+ *   gradient / first- and second-moment buffers of n floats — the optimizer the reference builds at
+ *   CGAT/lightning_module.py:328-344 (default --optim AdamW).  `lr` and `step` are DEVICE floats (a captured CUDA graph
+ *   replays with the current values; `step` is incremented before use); grad_scale multiplies the gradient on the way in
+ *   (the data-parallel average 1 / world size).  n % 4 == 0, buffers 16-byte aligned.
+ * cgat_l1_loss: loss[0] = mean_{i<n} |out[i*ldo] - target[i]| (nn.L1Loss on the first output column against the
+ *   normalised target, reference lightning_module.py:206-210, 237-240) and, if grad != NULL, its gradient w.r.t. the
+ *   (n_rows, n_cols) prediction (zero for padding rows >= n and columns >= 1).                                     */
+int cgat_sum_parts(const float* parts, int32_t n_parts, int64_t part_stride, float* out, int64_t n,
+                   int32_t accumulate, void* stream);
+int cgat_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float* step,
+                    float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+int cgat_l1_loss(const float* out, int64_t ldo, const float* target, int64_t n, float* loss, float* grad,
+                 int64_t ldg, int64_t n_rows, int32_t n_cols, void* stream);
 
 #ifdef __cplusplus
 }

