@@ -278,12 +278,34 @@ def forward_record(model, rank, world, dev, args, timed):
         runner(dev_pool[i % len(pool)])
     ms = timed(lambda i: runner(dev_pool[i % len(pool)]), steps)
     ms_e2e = timed(lambda i: runner(pin_pool[i % len(pool)])[:, 0].cpu(), steps)
+    # the same screening step fed from a crystal store RESIDENT IN HBM (cgat_b200/store.py): the host sends the ids of
+    # the batch's crystals, two kernel launches collate + pad the batch on the device
+    from cgat_b200 import store as cstore, synthetic
+    import numpy as np
+    lo, hi = wl["atoms"]
+    whole = synthetic.make_batch(2 * wl["crystals"], wl["max_nbr"], seed=5000 + rank, atoms_lo=lo, atoms_hi=hi)
+    st = cstore.CrystalStore.from_batch(whole).to(dev)
+    sels = [np.arange(0, wl["crystals"]), np.arange(wl["crystals"], 2 * wl["crystals"])]
+    pin_sel = [torch.as_tensor(sel).pin_memory() for sel in sels]
+
+    def store_step(i):
+        j = i % 2
+        sb = st.collate(sels[j], sel_dev=pin_sel[j].to(dev, non_blocking=True))
+        return runner(sb)[:, 0].cpu()
+    for i in range(4):
+        store_step(i)
+    ms_store = timed(store_step, steps)
     crystals = wl["crystals"] * world
     return {"metric": "crystals/sec forward (no_grad)", "workload": "cfg3_infer", "value": round(crystals * steps / (ms / 1e3), 2),
             "unit": "crystals/s", "ms_per_step": round(ms / steps, 4), "steps": steps, "crystals_per_gpu": wl["crystals"],
             "scaling": "weak", "parallelism": f"shard{world} (no collective)",
             "e2e": {"value": round(crystals * steps / (ms_e2e / 1e3), 2), "unit": "crystals/s",
-                    "h2d_bytes_per_step": pool[0].nbytes(), "d2h_bytes_per_step": wl["crystals"] * 4}}
+                    "h2d_bytes_per_step": pool[0].nbytes(), "d2h_bytes_per_step": wl["crystals"] * 4},
+            "e2e_device_store": {"value": round(crystals * steps / (ms_store / 1e3), 2), "unit": "crystals/s",
+                                 "h2d_bytes_per_step": wl["crystals"] * 8, "d2h_bytes_per_step": wl["crystals"] * 4,
+                                 "store_bytes_in_hbm": st.nbytes(),
+                                 "note": "crystal store resident in HBM; the host sends crystal ids only, "
+                                         "cgat_collate_plan / cgat_collate_fill build the padded batch on the device"}}
 
 
 KERNEL_NAMES = {  # profile key (ops.py `work`) -> kernel names in the ncu capture (profiles/*_kernel_metrics.json)

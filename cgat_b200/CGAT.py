@@ -89,22 +89,33 @@ class GATConvEdges(nn.Module):
     def __init__(self, in_channels, out_channels, nbr_channels, heads=1, concat=True, negative_slope=0.2,
                  dropout=0, bias=True, vector_attention=False, first=False, no_hyper=True, **kwargs):
         super().__init__()
-        if not no_hyper:
-            raise NotImplementedError(
-                "no_hyper=False (per-edge hypernetwork, reference CGAT.py:187-204) is not built yet: "
-                "it is unreachable from train-CGAT, which never forwards the flag (SURVEY.md §0.2)")
         self.in_channels, self.out_channels, self.nbr_channels = in_channels, out_channels, nbr_channels
         self.heads, self.vector_attention, self.first, self.no_hyper = heads, vector_attention, first, no_hyper
         width = 2 * in_channels + nbr_channels
         hidden = int(width / 1.5)
         self.MH_A = MultiHeadNetwork(width, out_channels if vector_attention else 1, hidden, heads)
         self.MH_M = MultiHeadNetwork(width, out_channels, hidden, heads)
-        self.Pooling_NN = SimpleNetwork(out_channels, out_channels, [out_channels])
+        if no_hyper:
+            self.Pooling_NN = SimpleNetwork(out_channels, out_channels, [out_channels])
+        else:                                                       # reference CGAT.py:187-204
+            net = H_Net_0 if first else H_Net
+            self.Pooling_NN = net(out_channels, 3, out_channels, out_channels, 2, out_channels, out_channels)
 
     def forward(self, x, edge_index, edge_attr, x_0, size=None):
-        """edge_attr may be per-edge (E, F_e) or the per-rank table (K+1, F_e): the live update only
-        looks at edge_attr itself."""
-        return self.Pooling_NN(edge_attr)
+        """no_hyper=True: edge_attr may be per-edge (E, F_e) or the per-rank table (K+1, F_e) — the live update only
+        looks at edge_attr itself (reference CGAT.py:224-225).  no_hyper=False (reference :209-223, :226-229): the
+        message MLP output weighted by a softmax over HEADS of the gate MLP, averaged over heads, drives a per-edge
+        hypernetwork update (H_Net_0(edge_attr, aggr) in the first layer, H_Net(edge_attr_0, edge_attr, aggr) after);
+        edge_attr is then the per-edge (E, F_e) tensor in the ORIGINAL edge order and x_0 = edge_attr_0."""
+        if self.no_hyper:
+            return self.Pooling_NN(edge_attr)
+        m = torch.cat([x.index_select(0, edge_index[0]), edge_attr, x.index_select(0, edge_index[1])], dim=1)
+        alpha = self.MH_A(m).exp()
+        alpha = alpha / alpha.sum(dim=1, keepdim=True)
+        aggr = (self.MH_M(m) * alpha).mean(dim=1)
+        if self.first:
+            return self.Pooling_NN(edge_attr, aggr)
+        return self.Pooling_NN(x_0, edge_attr, aggr)
 
 
 class GATConvNodes(nn.Module):
@@ -126,13 +137,14 @@ class GATConvNodes(nn.Module):
             net = H_Net_0 if first else H_Net
             self.Pooling_NN = net(out_channels, 3, out_channels, out_channels, 2, out_channels, out_channels)
 
-    def aggregate(self, x, edge_table, plan: EdgePlan):
+    def aggregate(self, x, edge_table, plan: EdgePlan, edge_ids=None):
         """(N, F): mean over heads of the attention-weighted messages arriving at each atom
-        (reference message() + scatter-add + update()'s head-mean, CGAT.py:319-329)."""
-        return ops.edge_attention(x, edge_table, plan, self.MH_A, self.MH_M, self.heads)
+        (reference message() + scatter-add + update()'s head-mean, CGAT.py:319-329).  edge_table: the per-rank
+        table (K+1, F_e), or — with edge_ids = plan.perm — per-edge features (E, F_e) in the original edge order."""
+        return ops.edge_attention(x, edge_table, plan, self.MH_A, self.MH_M, self.heads, edge_ids=edge_ids)
 
-    def forward(self, x, edge_table, plan: EdgePlan, x_0):
-        aggr = self.aggregate(x, edge_table, plan)
+    def forward(self, x, edge_table, plan: EdgePlan, x_0, edge_ids=None):
+        aggr = self.aggregate(x, edge_table, plan, edge_ids)
         if self.final:
             return aggr
         if self.first:
@@ -184,15 +196,26 @@ class CGAtNet(nn.Module):
         plan = build_edge_plan(batch.edge_index, batch.edge_attr, n_atoms)
         cry_plan = build_segment_plan(batch.batch, n_cry)
 
-        edge_table = self.nbr_embedding.weight                     # rank r -> e(r): reference :569
         x = self.embedding(batch.x)                                # reference :570
         x_0 = x
         last = len(self.graphs) - 1
-        for i, layer in enumerate(self.graphs):                    # reference :580-585
-            node_update = layer["Node"](x, edge_table, plan, x_0)
-            if i < last:  # the last layer's edge update is never read (its params get no gradient)
-                edge_table = edge_table + layer["Edge"](x, None, edge_table, None)
-            x = x + node_update
+        if self.no_hyper:
+            edge_table = self.nbr_embedding.weight                 # rank r -> e(r): reference :569
+            for i, layer in enumerate(self.graphs):                # reference :580-585
+                node_update = layer["Node"](x, edge_table, plan, x_0)
+                if i < last:  # the last layer's edge update is never read (its params get no gradient)
+                    edge_table = edge_table + layer["Edge"](x, None, edge_table, None)
+                x = x + node_update
+        else:
+            # per-edge hypernetwork variant: the edge embedding depends on node data, so it is a real (E, F_e) tensor
+            # (original edge order); the node attention reads it through plan.perm
+            edge_attr = self.nbr_embedding(batch.edge_attr)        # reference :569
+            edge_attr_0 = edge_attr
+            for i, layer in enumerate(self.graphs):
+                node_update = layer["Node"](x, edge_attr, plan, x_0, edge_ids=plan.perm)
+                if i < last:
+                    edge_attr = edge_attr + layer["Edge"](x, batch.edge_index, edge_attr, edge_attr_0)
+                x = x + node_update
 
         comp = self.roost(weights, r_fea, self_idx, nbr_idx, r_cry, n_crystals=n_cry)   # :587
         pooled = self.cry_pool(x, comp, batch.batch, plan=cry_plan)                      # :588

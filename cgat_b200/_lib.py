@@ -69,6 +69,8 @@ SIGNATURES = {
     "cgat_sum_parts": (ctypes.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P]),
     "cgat_adamw_flat": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F32, _F32, _F32, _F32, _F32, _P]),
     "cgat_l1_loss": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I32, _P]),
+    "cgat_collate_plan": (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P]),
+    "cgat_collate_fill": (ctypes.c_int, [_P, _I64] + [_P] * 8 + [_I32, _I32] + [_P] * 13 + [_I64] * 6 + [_P]),
 }
 
 

@@ -49,4 +49,29 @@ inline int hyper_chunk(int64_t n_atoms, int f) {
   return oc;
 }
 
+// Partial-result slots of the hyper activation-gradient kernels (cgat_hyper_rowscale[_f16]).  Work items are
+// (atom tile, chunk of output channels), chunk fastest, dealt to the CTAs as contiguous ranges; a CTA accumulates the
+// consecutive chunks of one tile in registers and writes ONE partial row block per (CTA, tile) into slot
+// (this CTA) - (first CTA that touches the tile).  hyper_slots() bounds that slot count: with >= per = floor(items /
+// grid) items per CTA a tile's n_chunks items meet at most ceil(n_chunks / per) + 1 CTAs.  (Round 1 wrote one partial
+// per chunk: 16 x N x F floats per launch at the bench size instead of 5, all re-read by the partial sum.)
+inline int hyper_grid(int64_t n_atoms, int f) {
+  const int64_t n_items = ((n_atoms + 127) / 128) * (f / hyper_chunk(n_atoms, f));
+  return (int)(n_items < kNumSMs ? (n_items > 0 ? n_items : 1) : kNumSMs);
+}
+inline int hyper_slots(int64_t n_atoms, int f) {
+  const int n_chunks = f / hyper_chunk(n_atoms, f);
+  const int64_t n_items = ((n_atoms + 127) / 128) * n_chunks;
+  const int64_t per = n_items / hyper_grid(n_atoms, f);
+  const int64_t s = per > 0 ? (n_chunks + per - 1) / per + 1 : n_chunks;
+  return (int)(s < n_chunks ? s : n_chunks);
+}
+// first CTA whose item range [n_items*b/G, n_items*(b+1)/G) contains item i
+__host__ __device__ inline int hyper_cta_of_item(int64_t i, int64_t n_items, int G) {
+  int b = (int)((i * G) / n_items);
+  while (b + 1 < G && (n_items * (b + 1)) / G <= i) ++b;
+  while (b > 0 && (n_items * b) / G > i) --b;
+  return b;
+}
+
 }  // namespace cgat

@@ -41,7 +41,7 @@ template <int F, int kMode>
 __global__ void __launch_bounds__(Hyper16Cfg<F>::kThreads, 1)
 hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
                         const float* __restrict__ e_term2, const float* __restrict__ w_bias,
-                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
+                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc, int n_slots) {
   using Cfg = Hyper16Cfg<F>;
   static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
   extern __shared__ uint8_t smem_raw[];
@@ -97,16 +97,20 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ocount = 0;
+    float y[QF];
     for (int item = item_lo; item < item_hi; ++item) {
       const int tile = item / n_chunks, chunk = item - tile * n_chunks;
       const int n = tile * 128 + row;
       const bool valid = n < n_atoms;
-      float y[QF];  // kMode 0: this atom's quarter y_in row; kMode 1: the running partial sums over o
+      // kMode 0: this atom's quarter y_in row; kMode 1: the running partial sums over o, carried across the
+      // consecutive chunks of one tile (a new run starts with the CTA's first item or a tile's first chunk)
+      if (kMode == 0 || item == item_lo || chunk == 0) {
 #pragma unroll
-      for (int j = 0; j < QF / 4; ++j) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * QF) + j);
-        y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+        for (int j = 0; j < QF / 4; ++j) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * QF) + j);
+          y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+        }
       }
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
         const int o = chunk * oc + oi;
@@ -177,10 +181,19 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
         }
         asm volatile("bar.sync 3, %0;" ::"n"(Cfg::kEpiThreads) : "memory");  // `red` may be overwritten by the next item
       }
-      if (kMode == 1 && valid) {
-        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F + grp * QF);
+      if (kMode == 1 && valid && (item + 1 == item_hi || chunk == n_chunks - 1)) {
+        // end of this CTA's run on the tile: one partial per (CTA, tile); the CTA that finishes the tile also clears
+        // the slots nobody used (the caller sums all n_slots)
+        const int slot = (int)blockIdx.x - hyper_cta_of_item((int64_t)tile * n_chunks, n_items, (int)gridDim.x);
+        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)slot * n_atoms + n) * F + grp * QF);
 #pragma unroll
         for (int j = 0; j < QF / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        if (chunk == n_chunks - 1)
+          for (int sl = slot + 1; sl < n_slots; ++sl) {
+            float4* z4 = reinterpret_cast<float4*>(y_out + ((int64_t)sl * n_atoms + n) * F + grp * QF);
+#pragma unroll
+            for (int j = 0; j < QF / 4; ++j) z4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
       }
     }
   } else if (warp < kMmaWarp) {
@@ -313,12 +326,10 @@ int launch_hyper16(const float* z, const float* y_in, const float* e_term, const
                                    Cfg::kSmemBytes));
     configured = true;
   }
-  const int n_tiles = (int)((n_atoms + 127) / 128);
   const int oc = hyper_chunk(n_atoms, f);
-  const int n_items = n_tiles * (f / oc);
-  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  const int grid = hyper_grid(n_atoms, f);
   hyper_rowdot_f16_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc);
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f));
   return check_launch(kMode == 0 ? "hyper_rowdot_f16_kernel" : "hyper_rowscale_f16_kernel");
 }
 }  // namespace

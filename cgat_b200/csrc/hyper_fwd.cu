@@ -52,7 +52,7 @@ template <int F, int kMode, bool kTS>
 __global__ void __launch_bounds__(HyperCfg<F>::kThreads, 1)
 hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
                         const float* __restrict__ e_term2, const float* __restrict__ w_bias,
-                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc) {
+                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc, int n_slots) {
   using Cfg = HyperCfg<F, kTS>;
   static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
   constexpr uint32_t kAHiCol = 2 * F, kALoCol = 3 * F;  // kTS: operand columns behind the accumulator
@@ -107,16 +107,19 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
     const int grp = warp >> 2;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ocount = 0;
+    float y[HF];  // kMode 0: this atom's half y_in row; kMode 1: the running partial sums over o
     for (int item = item_lo; item < item_hi; ++item) {
       const int tile = item / n_chunks, chunk = item - tile * n_chunks;
       const int n = tile * 128 + (warp & 3) * 32 + lane;
       const bool valid = n < n_atoms;
-      float y[HF];  // kMode 0: this atom's half y_in row; kMode 1: the running partial sums over o
+      // kMode 1: the sums are carried across the consecutive chunks of one tile (see hyper_slots, common.cuh)
+      if (kMode == 0 || item == item_lo || chunk == 0) {
 #pragma unroll
-      for (int j = 0; j < HF / 4; ++j) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * HF) + j);
-        y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+        for (int j = 0; j < HF / 4; ++j) {
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * HF) + j);
+          y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+        }
       }
       float accs[16];  // kMode 0: half dot products of this item's <= 16 outputs
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
@@ -173,10 +176,17 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
             if (q < oc) yo[q] = (accs[q] + __ldcg(yo + q)) + (__ldg(e1 + q) + (e2 ? __ldg(e2 + q) : 0.f));
         }
       }
-      if (kMode == 1 && valid) {
-        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)chunk * n_atoms + n) * F + grp * HF);
+      if (kMode == 1 && valid && (item + 1 == item_hi || chunk == n_chunks - 1)) {
+        const int slot = (int)blockIdx.x - hyper_cta_of_item((int64_t)tile * n_chunks, n_items, (int)gridDim.x);
+        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)slot * n_atoms + n) * F + grp * HF);
 #pragma unroll
         for (int j = 0; j < HF / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+        if (chunk == n_chunks - 1)
+          for (int sl = slot + 1; sl < n_slots; ++sl) {
+            float4* z4 = reinterpret_cast<float4*>(y_out + ((int64_t)sl * n_atoms + n) * F + grp * HF);
+#pragma unroll
+            for (int j = 0; j < HF / 4; ++j) z4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
       }
     }
   } else if (warp < 12) {
@@ -337,12 +347,10 @@ int launch_hyper_impl(const float* z, const float* y_in, const float* e_term, co
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
-  const int n_tiles = (int)((n_atoms + 127) / 128);
   const int oc = hyper_chunk(n_atoms, f);
-  const int n_items = n_tiles * (f / oc);
-  const int grid = n_items < kNumSMs ? n_items : kNumSMs;
+  const int grid = hyper_grid(n_atoms, f);
   hyper_rowdot_fwd_kernel<128, kMode, kTS><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc);
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f));
   return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");
 }
 
@@ -381,7 +389,7 @@ extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const fl
 }
 
 // number of partial results cgat_hyper_rowscale writes for this problem size
-extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { return f / hyper_chunk(n_atoms, f); }
+extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { return hyper_slots(n_atoms, f); }
 
 // partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m] + w_bias[o*F+j]);  sum over c = the
 // result (w_bias optional: the bias of the predicted weights when a = z, NULL when a = y).

@@ -33,9 +33,13 @@ _ALIGN = 128   # floats: every parameter's slice of the flat buffers starts on a
 def live_parameters(model):
     """(name, param) pairs that take part in training; dead parameters are skipped."""
     n_graph = len(model.graphs)
+    hyper_edges = not getattr(model, "no_hyper", True)   # no_hyper=False: the Edge attention is live, except the last layer's
     out = []
     for name, p in model.named_parameters():
-        if _DEAD.search(name) or name.startswith(f"graphs.{n_graph - 1}.Edge.Pooling_NN."):
+        if hyper_edges:
+            if name.startswith(f"graphs.{n_graph - 1}.Edge."):
+                continue
+        elif _DEAD.search(name) or name.startswith(f"graphs.{n_graph - 1}.Edge.Pooling_NN."):
             continue
         out.append((name, p))
     return out

@@ -107,7 +107,7 @@ def multi_head_mlp(fea, w_in, b_in, w_out, b_out, heads):
     return out.transpose(0, 1)                                                                # (n, H, Out)
 
 
-def edge_attention_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
+def edge_attention_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads, edge_ids=None):
     """Node-attention aggregation, reference CGAT/CGAT.py:319-329 (Appendix A of SURVEY.md) — library GEMMs +
     the segmented-softmax kernel.  Used for the shapes the fused kernel is not instantiated for and as
     the recompute path of its backward.
@@ -122,8 +122,9 @@ def edge_attention_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2
     w1 = torch.cat([w1a, w1m], dim=0)                              # (2*H*Hd, 2F+Fe)
     p_dst = x @ w1[:, :f].t()                                      # (N, 2*H*Hd)
     p_src = x @ w1[:, f + fe:].t()
-    t_rank = torch.addmm(torch.cat([b1a, b1m]), edge_table, w1[:, f:f + fe].t())   # (K+1, 2*H*Hd)
-    pre = p_dst.index_select(0, plan.dst) + p_src.index_select(0, plan.src) + t_rank.index_select(0, plan.rank)
+    t_rank = torch.addmm(torch.cat([b1a, b1m]), edge_table, w1[:, f:f + fe].t())   # (K+1, 2*H*Hd) / (E, 2*H*Hd)
+    pre = (p_dst.index_select(0, plan.dst) + p_src.index_select(0, plan.src)
+           + t_rank.index_select(0, plan.rank if edge_ids is None else edge_ids))
     hid = torch.nn.functional.leaky_relu(pre, LEAKY_SLOPE)
     e = hid.shape[0]
     hid_a = hid[:, :hhd].view(e, heads, hd).transpose(0, 1)        # (H, E, Hd)
@@ -709,13 +710,15 @@ def edge_attention_heads_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b
     return seg_softmax(gate, msg, ptr=plan.rowptr, seg_of_row=plan.dst, n_seg=n, eps=1e-16)
 
 
-def edge_attention(x, edge_table, plan, mh_a, mh_m, heads):
+def edge_attention(x, edge_table, plan, mh_a, mh_m, heads, edge_ids=None):
     """(N, F): mean over heads of the attention-weighted messages arriving at each atom (reference
     GATConvNodes.message + aggregate + the head-mean of update, CGAT/CGAT.py:319-329).  `mh_a`, `mh_m` are
-    the gate / message MultiHeadNetwork modules (parameters fc_in/fc_out in the reference's Conv1d layout)."""
+    the gate / message MultiHeadNetwork modules (parameters fc_in/fc_out in the reference's Conv1d layout).
+    edge_ids (no_hyper=False only): edge_table holds per-EDGE features and row edge_ids[t] belongs to the t-th edge of
+    the destination-sorted order; that variant runs the unfused formulation (the fused kernel gathers a per-rank table)."""
     f = x.shape[1]
     hd = mh_a.hidden_dim
-    fused_ok = (_FUSED and x.is_cuda and f == 128 and mh_a.output_dim == f and mh_m.output_dim == f
+    fused_ok = (_FUSED and edge_ids is None and x.is_cuda and f == 128 and mh_a.output_dim == f and mh_m.output_dim == f
                 and hd % 128 == 0 and hd <= 256 and heads <= 8 and edge_table.shape[1] % 4 == 0
                 and edge_table.shape[0] <= 32)
     if fused_ok:
@@ -727,4 +730,4 @@ def edge_attention(x, edge_table, plan, mh_a, mh_m, heads):
                                         packed_kmajor(mh_m.fc_out.weight, **pk), plan, heads, f16)
         return out.mean(dim=1)
     return edge_attention_unfused(x, edge_table, plan, mh_a.w_in(), mh_a.fc_in.bias, mh_a.w_out(), mh_a.fc_out.bias,
-                                  mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads)
+                                  mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads, edge_ids)

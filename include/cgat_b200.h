@@ -265,6 +265,27 @@ int cgat_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, con
 int cgat_l1_loss(const float* out, int64_t ldo, const float* target, int64_t n, float* loss, float* grad,
                  int64_t ldg, int64_t n_rows, int32_t n_cols, void* stream);
 
+/* ---- device-side collation ------------------------------------------------------
+ * Builds the collated, bucket-padded batch CGAtNet.forward takes from a crystal store resident in HBM (packed ragged
+ * arrays, cgat_b200/store.py) and a list of selected crystals — what the reference does per batch on the host with
+ * torch_geometric Batch.from_data_list (CGAT/lightning_module.py:199-200), collate_batch (CGAT/roost_message.py:
+ * 400-458) and the Roost pair lists of CompositionData.__getitem__ (CGAT/data.py:89-96).  Bit-exact against that.
+ *   store: x (A, d) atom features; nbr / rank (A, k) int32 LOCAL neighbour index inside the crystal / shell rank;
+ *          atom_ptr (C+1); comp_w (M), comp_fea (M, d) distinct-element weights / features; comp_ptr (C+1); y (C).
+ *   cgat_collate_plan: exclusive scans (n_sel+1, int64) of the selected crystals' atom / element / pair counts.
+ *   cgat_collate_fill: out_x (n_pad, d), edge_index (2, n_pad*k), edge_attr (n_pad*k), batch (n_pad), out_y (n_sel+1),
+ *          out_w (nc_pad), out_fea (nc_pad, d), self_idx / nbr_idx (mc_pad), cry_idx (nc_pad); rows beyond the real
+ *          totals form ONE dummy crystal (id n_sel) exactly like cgat_b200/batching.pad_batch.                     */
+int cgat_collate_plan(const int64_t* sel, int64_t n_sel, const int64_t* atom_ptr, const int64_t* comp_ptr,
+                      int64_t* atom_off, int64_t* comp_off, int64_t* pair_off, void* stream);
+int cgat_collate_fill(const int64_t* sel, int64_t n_sel, const float* x, const int32_t* nbr, const int32_t* rank,
+                      const int64_t* atom_ptr, const float* comp_w, const float* comp_fea, const int64_t* comp_ptr,
+                      const float* y, int32_t d, int32_t k, const int64_t* atom_off, const int64_t* comp_off,
+                      const int64_t* pair_off, float* out_x, int64_t* edge_index, int64_t* edge_attr, int64_t* batch,
+                      float* out_y, float* out_w, float* out_fea, int64_t* self_idx, int64_t* nbr_idx,
+                      int64_t* cry_idx, int64_t n_atoms, int64_t n_pad, int64_t n_comp, int64_t nc_pad,
+                      int64_t n_pairs, int64_t mc_pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

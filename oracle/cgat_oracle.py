@@ -146,10 +146,25 @@ def gat_conv_nodes(sd, pre, x, edge_index, edge_attr, x_0, heads, first, clamp_d
     return hyper_fc_apply(sd, pre + "Pooling_NN.Hyper.", hyper_in, aggr)
 
 
-def gat_conv_edges(sd, pre, x, edge_index, edge_attr, heads, as_written=False):
-    """GATConvEdges.forward, CGAT/CGAT.py:208-230, no_hyper=True branch.  Lines :209-223 compute an
-    attention whose result is overwritten at :224-225; `as_written=True` executes that dead work too
-    (used only to time the reference 'as written')."""
+def gat_conv_edges(sd, pre, x, edge_index, edge_attr, heads, as_written=False, no_hyper=True, first=False,
+                   edge_attr_0=None, clamp_damping=True):
+    """GATConvEdges.forward, CGAT/CGAT.py:208-230.  no_hyper=True: lines :209-223 compute an attention whose
+    result is overwritten at :224-225; `as_written=True` executes that dead work too (used only to time the
+    reference 'as written').  no_hyper=False (:226-229): the head-softmaxed message drives a per-EDGE hypernetwork
+    update, H_Net_0(h_0=edge_attr, x=aggr) in the first layer, H_Net(h_0=edge_attr_0, h_t=edge_attr, x=aggr) after."""
+    if not no_hyper:
+        m = torch.cat([x[edge_index[0]], edge_attr, x[edge_index[1]]], dim=-1)     # :209-211 (x_i = x[source] here)
+        a = multi_head_network(sd, pre + "MH_A.", m, heads).exp()                  # :212, :214
+        mm = multi_head_network(sd, pre + "MH_M.", m, heads)                       # :213
+        a = a / a.sum(dim=1, keepdim=True)                                         # :216-219 (softmax over HEADS)
+        aggr = (mm * a).mean(dim=1)                                                # :222-223
+        if first:                                                                  # :226-227
+            return hyper_fc_apply(sd, pre + "Pooling_NN.Hyper.", edge_attr, aggr)
+        d = sd[pre + "Pooling_NN.damping"]                                         # :228-229, Hypernetworksmp.py:309-313
+        if clamp_damping:
+            with torch.no_grad():
+                d.data = d.data.clamp(0.0, 1.0)
+        return hyper_fc_apply(sd, pre + "Pooling_NN.Hyper.", d * edge_attr_0 + (1 - d) * aggr, aggr)
     if as_written:
         m = torch.cat([x[edge_index[0]], edge_attr, x[edge_index[1]]], dim=-1)
         a = multi_head_network(sd, pre + "MH_A.", m, heads).exp()
@@ -208,10 +223,12 @@ def cgat_forward(sd, cfg, graph, roost_in, last_layer=True, return_graph_embeddi
     edge_attr = sd["nbr_embedding.weight"][graph.edge_attr]                        # :569
     x = F.linear(graph.x, sd["embedding.weight"])                                 # :570
     x_0 = x                                                                        # :571
+    edge_attr_0 = edge_attr                                                        # :574
+    no_hyper = cfg.get("no_hyper", True)
     for l in range(n_graph):                                                       # :580-585
         node_upd = gat_conv_nodes(sd, f"graphs.{l}.Node.", x, edge_index, edge_attr, x_0, heads, l == 0)
         edge_attr = edge_attr + gat_conv_edges(sd, f"graphs.{l}.Edge.", x, edge_index, edge_attr, heads,
-                                               as_written)
+                                               as_written, no_hyper, l == 0, edge_attr_0)
         x = x + node_upd
         inter[f"x{l + 1}"] = x
     weights, fea, self_idx, nbr_idx, crystal_idx = roost_in

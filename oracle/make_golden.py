@@ -8,6 +8,7 @@ cgat_b200/synthetic.py and stores the outputs and a digest of the gradients.  In
 are NOT stored: they are regenerated from their seeds on the other side.
 
     python oracle/make_golden.py            # rewrites every fixture
+    python oracle/make_golden.py edge_hypernet      # only the named ones
 """
 from __future__ import annotations
 
@@ -45,6 +46,10 @@ CASES = {
                             rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
                             n_graph_roost=3),
                        dict(n_crystals=2, max_nbr=24, seed=4, atoms_lo=200, atoms_hi=256), 4),
+    "edge_hypernet": (dict(elem_fea_len=64, n_graph=3, msg_heads=2, neighbor_number=8, mean_pooling=False,
+                           rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
+                           n_graph_roost=1, no_hyper=False),
+                      dict(n_crystals=8, max_nbr=8, seed=5), 5),
 }
 
 # gradient tensors stored in full (small); every other gradient is stored as (sum, abs-sum, l2)
@@ -97,7 +102,10 @@ def run_case(name, ref):
 def main():
     ref = standins.import_reference()
     os.makedirs(os.path.join(ROOT, "tests", "golden"), exist_ok=True)
+    only = set(sys.argv[1:])          # python oracle/make_golden.py [case ...]: default every fixture
     for name in CASES:
+        if only and name not in only:
+            continue
         rec = run_case(name, ref)
         np.savez_compressed(os.path.join(ROOT, "tests", "golden", f"ref_{name}.npz"), **rec)
 

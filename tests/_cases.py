@@ -28,6 +28,10 @@ CASES = {
                             rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
                             n_graph_roost=3),
                        dict(n_crystals=2, max_nbr=24, seed=4, atoms_lo=200, atoms_hi=256), 4),
+    "edge_hypernet": (dict(elem_fea_len=64, n_graph=3, msg_heads=2, neighbor_number=8, mean_pooling=False,
+                           rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
+                           n_graph_roost=1, no_hyper=False),
+                      dict(n_crystals=8, max_nbr=8, seed=5), 5),
 }
 
 ATOL, RTOL = 1e-4, 1e-3  # BASELINE.json north_star: fp32 predictions and gradients
@@ -44,7 +48,7 @@ def golden_shapes(gold):
 
 def oracle_cfg(mkw):
     return dict(n_graph=mkw["n_graph"], msg_heads=mkw["msg_heads"], mean_pooling=mkw["mean_pooling"],
-                rezero=mkw["rezero"])
+                rezero=mkw["rezero"], no_hyper=mkw.get("no_hyper", True))
 
 
 def training_scalar(out, y):
