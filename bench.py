@@ -224,9 +224,10 @@ def run_ours(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:   # reported at N=1 only (the other ranks would idle)
         cpu = cpu_baseline(wl, net_kw, train)
     if world > 1:
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
     if rank != 0:
+        _leave(world)
         return
     n_atoms = int(sum(int(sb.n_atoms[:n_real].sum()) for sb in pool) / len(pool))
     graph_cfg = None
@@ -261,7 +262,19 @@ def run_ours(args):
     }
     if fwd is not None:
         line["forward"] = fwd   # BASELINE.json's metric is "fwd & train step": the forward half, same process, same N
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    _leave(world)
+
+
+def _leave(world):
+    """Several ranks: leave without tearing the process group down.  destroy_process_group() blocks while CUDA graphs
+    that contain NCCL nodes are alive (measured: scripts/nccl_graph_probe.py mode A completes every replay correctly
+    and then hangs in destroy), and releasing the graphs first depends on garbage-collection order; every rank has
+    passed the final barrier, the results are printed, so the processes simply exit."""
+    if world > 1:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def forward_record(model, rank, world, dev, args, timed):

@@ -67,6 +67,7 @@ SIGNATURES = {
     "cgat_edge_attn_wgrad_splits": (_I32, [_I32]),
     "cgat_edge_attn_wgrad": (ctypes.c_int, [_P] * 8 + [_I64, _I32, _I32, _I32, _P]),
     "cgat_sum_parts": (ctypes.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P]),
+    "cgat_sum_parts_bias_act": (ctypes.c_int, [_P, _I32, _I64, _P, _P, _I64, _I64, _I32, _P]),
     "cgat_adamw_flat": (ctypes.c_int, [_P, _P, _P, _P, _I64, _P, _P, _F32, _F32, _F32, _F32, _F32, _P]),
     "cgat_l1_loss": (ctypes.c_int, [_P, _I64, _P, _I64, _P, _P, _I64, _I64, _I32, _P]),
     "cgat_collate_plan": (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _P]),

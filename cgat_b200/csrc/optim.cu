@@ -54,6 +54,36 @@ __global__ void __launch_bounds__(kSumThreads) sum_parts_scalar_kernel(const flo
   }
 }
 
+// out[m, n] = act(sum_p parts[p][m, n] + bias[n]): the epilogue of a split-K GEMM whose partial tiles were written by
+// cgat_gemm3x_nt_splitk (bias / activation cannot be applied per part).  n_cols % 4 == 0.
+__global__ void __launch_bounds__(kSumThreads) sum_parts_bias_act_kernel(const float* __restrict__ parts, int n_parts,
+                                                                         int64_t stride, const float* __restrict__ bias,
+                                                                         float* __restrict__ out, int64_t n4,
+                                                                         int n_cols4, int act) {
+  for (int64_t i = (int64_t)blockIdx.x * kSumThreads + threadIdx.x; i < n4; i += (int64_t)gridDim.x * kSumThreads) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* src = reinterpret_cast<const float4*>(parts) + i;
+    for (int p = 0; p < n_parts; ++p) {
+      const float4 a = __ldg(src + (int64_t)p * (stride >> 2));
+      acc.x += a.x, acc.y += a.y, acc.z += a.z, acc.w += a.w;
+    }
+    if (bias != nullptr) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(bias) + (int)(i % n_cols4));
+      acc.x += b.x, acc.y += b.y, acc.z += b.z, acc.w += b.w;
+    }
+    float* a = reinterpret_cast<float*>(&acc);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = a[j];
+      if (act == 1) v = v > 0.f ? v : 0.01f * v;
+      else if (act == 2) v = tanhf(v);
+      else if (act == 3) v = fmaxf(v, 0.f);
+      a[j] = v;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+  }
+}
+
 __global__ void adamw_tick_kernel(float* __restrict__ step) { step[0] += 1.f; }
 
 constexpr int kAdamThreads = 256;
@@ -144,6 +174,24 @@ extern "C" int cgat_sum_parts(const float* parts, int32_t n_parts, int64_t part_
     else sum_parts_scalar_kernel<false><<<(unsigned)blocks, kSumThreads, 0, stream>>>(parts, n_parts, part_stride, out, n);
   }
   return check_launch("sum_parts_kernel");
+}
+
+// out (M, N) = act(sum_p parts[p] + bias[N]) for contiguous (M, N) parts `part_stride` floats apart; N % 4 == 0.
+// act: 0 none, 1 LeakyReLU(0.01), 2 tanh, 3 ReLU (as cgat_gemm3x_nt).
+extern "C" int cgat_sum_parts_bias_act(const float* parts, int32_t n_parts, int64_t part_stride, const float* bias,
+                                       float* out, int64_t M, int64_t N, int32_t act, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (M <= 0 || N <= 0) return 0;
+  if ((N & 3) || (part_stride & 3) || n_parts < 1 ||
+      ((reinterpret_cast<uintptr_t>(parts) | reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15))
+    return fail(-2, "cgat_sum_parts_bias_act: N and part_stride must be multiples of 4, buffers 16-byte aligned");
+  const int64_t work = M * N / 4;
+  int64_t blocks = ceil_div(work, kSumThreads);
+  const int64_t cap = (int64_t)kNumSMs * 16;
+  if (blocks > cap) blocks = cap;
+  sum_parts_bias_act_kernel<<<(unsigned)blocks, kSumThreads, 0, stream>>>(parts, n_parts, part_stride, bias, out, work,
+                                                                         (int)(N / 4), act);
+  return check_launch("sum_parts_bias_act_kernel");
 }
 
 // One AdamW step over flat buffers of n floats (n % 4 == 0, 16-byte aligned).  `step` (device float) is incremented

@@ -148,6 +148,20 @@ def gemm3x(a, w, bias=None, act=0, out=None):
         out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     if not a.is_cuda:
         raise _lib.CgatLibraryError("cgat_b200 kernels need CUDA tensors (there is no CPU path)")
+    tiles = ((M + 127) // 128) * ((N + (63 if N <= 64 else 127)) // (64 if N <= 64 else 128))
+    if tiles <= 74 and K >= 256 and N % 4 == 0 and out.is_contiguous():
+        # few output tiles and a long contraction (the Roost / crystal-pool / output MLPs: M = crystals or elements):
+        # one 128 x 128 tile per CTA would leave most SMs idle and walk K serially, so split K over CTAs and apply
+        # bias + activation while the parts are summed
+        n_split = plan_split(K, max(2, min(K // 128, 148 // tiles)))
+        if n_split > 1:
+            part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
+            _lib.call("cgat_gemm3x_nt_splitk", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), part.data_ptr(), N,
+                      M * N, M, N, K, n_split, _lib.stream(),
+                      work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))
+            _lib.call("cgat_sum_parts_bias_act", _lib.ptr(part), n_split, M * N, _lib.ptr(bias), _lib.ptr(out), M, N, act,
+                      _lib.stream(), work=dict(key="sum_parts", bound="hbm", bytes=4.0 * M * N * (n_split + 1)))
+            return out
     _lib.call("cgat_gemm3x_nt", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _lib.ptr(bias),
               out.data_ptr(), out.stride(0), M, N, K, act, _lib.stream(),
               work=dict(key="gemm3x_nt", bound="tensor", flops=2.0 * M * N * K))

@@ -260,6 +260,10 @@ int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, con
  *   (n_rows, n_cols) prediction (zero for padding rows >= n and columns >= 1).                                     */
 int cgat_sum_parts(const float* parts, int32_t n_parts, int64_t part_stride, float* out, int64_t n,
                    int32_t accumulate, void* stream);
+/* out (M, N) = act(sum_p parts[p] + bias[N]): the epilogue of cgat_gemm3x_nt_splitk when the layer has a bias /
+ * activation (few-tile GEMMs of the Roost / pool / output MLPs are split over K to fill the SMs).          */
+int cgat_sum_parts_bias_act(const float* parts, int32_t n_parts, int64_t part_stride, const float* bias, float* out,
+                            int64_t M, int64_t N, int32_t act, void* stream);
 int cgat_adamw_flat(float* p, const float* g, float* m, float* v, int64_t n, const float* lr, float* step,
                     float beta1, float beta2, float eps, float weight_decay, float grad_scale, void* stream);
 int cgat_l1_loss(const float* out, int64_t ldo, const float* target, int64_t n, float* loss, float* grad,
