@@ -19,7 +19,7 @@ _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
 
-ABI_VERSION = 3  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
+ABI_VERSION = 4  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
 
 # name -> (restype, argtypes); must list every symbol declared in include/cgat_b200.h
 SIGNATURES = {
@@ -43,7 +43,8 @@ SIGNATURES = {
     "cgat_pack_kmajor_f16s": (ctypes.c_int, [_P, _I64, _I64, _I64, _I32, _F32, _F32, _P, _P]),
     "cgat_edge_attn_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                               _I32, _I32, _F32, _P]),
-    "cgat_edge_attn_bwd_prep_f16": (ctypes.c_int, [_P] * 18 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_bwd_prep_f16": (ctypes.c_int, [_P] * 19 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_wgrad_f16": (ctypes.c_int, [_P] * 9 + [_I64, _I32, _I32, _I32, _P]),
     "cgat_hyper_rowdot_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowscale_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowdot_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
@@ -54,11 +55,13 @@ SIGNATURES = {
     "cgat_gemm3x_tn_batched": (ctypes.c_int, [_P, _P, _I32, _I64, _I64, _P, _P, _I64, _I64, _I64, _I32, _P]),
     "cgat_hyper_rowscale_parts": (_I32, [_I64, _I32]),
     "cgat_hyper_rowscale": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_rowscale_f16_amax": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_wgrad_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_wgrad_splits": (_I32, [_I64]),
     "cgat_hyper_wgrad": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_edge_attn_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                           _I32, _I32, _F32, _P]),
-    "cgat_edge_attn_bwd_prep": (ctypes.c_int, [_P] * 18 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_bwd_prep": (ctypes.c_int, [_P] * 19 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
     "cgat_edge_attn_grid": (_I32, [_I64]),
     "cgat_edge_attn_dgrad_grid": (_I32, [_I64]),
     "cgat_edge_attn_dgrad": (ctypes.c_int, [_P] * 10 + [_I64, _I32, _P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P]),

@@ -69,6 +69,7 @@ struct EdgeArgs {
   float* d_msg;         // backward-prep: dL/d v_t,h (E, H, F)
   uint32_t* signs;      // backward-prep: [2][H][kcn][E] LeakyReLU side of the 32 hidden units of a chunk
   float* bias_sums;     // backward-prep (optional): (grid, 2, H, F) per-CTA column sums of d_msg | d_gate = dL/d b2
+  unsigned int* dz_amax;  // backward-prep (optional): max |d_gate|, |d_msg| as float bits (range of the f16 wgrad / dgrad)
   int n_atoms, n_edges, heads, hd;
   float eps;
   int n_stages;         // operand ring depth: 3, or 2 with L1 prefetch of the gathered rows (f16 path)
@@ -188,6 +189,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int hf = H * kEF;
     uint32_t hcount = 0;
+    float dz_max = 0.f;
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int e0 = e_lo + tile * kET;
       const int nv = min(kET, e_hi - e0);
@@ -289,6 +291,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                 pm[(int64_t)(cc * 8 + j) * hf] = ag;
                 pg[(int64_t)(cc * 8 + j) * hf] = dg;
                 sum_m += ag, sum_g += dg;
+                dz_max = fmaxf(dz_max, fmaxf(fabsf(ag), fabsf(dg)));
               }
             }
           }
@@ -299,6 +302,12 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           carry[((grp * 2 + 1) * kEMaxHeads + h) * kEF + c] += sum_g;
         }
       }
+    }
+    if (kMode == 1 && g.dz_amax != nullptr) {
+      // order-independent maximum (non-negative floats compare like their bit patterns): deterministic
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) dz_max = fmaxf(dz_max, __shfl_xor_sync(0xffffffffu, dz_max, o));
+      if (lane == 0) atomicMax(g.dz_amax, __float_as_uint(dz_max));
     }
   } else if (warp < kEMmaWarp) {
     // ---------------------------------------------------------------- producers
@@ -596,7 +605,7 @@ int edge_fwd_impl(const float* P, const float* T, const int32_t* rowptr, const i
   }
   if (n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-             nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
+             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
   return launch_edge<0, kF16>(a, stream);
 }
 
@@ -605,15 +614,16 @@ int edge_bwd_prep_impl(const float* P, const float* T, const int32_t* rowptr, co
                        const int32_t* rank, const float* w2a_packed, const float* w2m_packed, const float* b2a,
                        const float* b2m, const float* out, const float* seg_max, const float* seg_den,
                        const float* g_out, float* d_gate, float* d_msg, uint32_t* signs, float* bias_sums,
-                       int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps,
+                       float* dz_amax, int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps,
                        void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (int e = check_edge_args(n_atoms, n_edges, heads, f, hd)) return e;
   if (kF16 && (hd & 63)) return fail(-2, "cgat_edge_attn_bwd_prep_f16: hidden width must be a multiple of 64");
+  if (dz_amax) CGAT_CUDA(cudaMemsetAsync(dz_amax, 0, sizeof(float), stream));
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
              const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs, bias_sums,
-             (int)n_atoms, (int)n_edges, heads, hd, eps};
+             reinterpret_cast<unsigned int*>(dz_amax), (int)n_atoms, (int)n_edges, heads, hd, eps};
   return launch_edge<1, kF16>(a, stream);
 }
 }  // namespace
@@ -650,18 +660,18 @@ extern "C" int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int
                                        const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                                        const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                                        const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                                       float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                       float* d_msg, uint32_t* signs, float* bias_sums, float* dz_amax, int64_t n_atoms, int64_t n_edges, int32_t heads,
                                        int32_t f, int32_t hd, float eps, void* stream_) {
   return edge_bwd_prep_impl<false>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-                                   g_out, d_gate, d_msg, signs, bias_sums, n_atoms, n_edges, heads, f, hd, eps, stream_);
+                                   g_out, d_gate, d_msg, signs, bias_sums, dz_amax, n_atoms, n_edges, heads, f, hd, eps, stream_);
 }
 
 extern "C" int cgat_edge_attn_bwd_prep_f16(const float* P, const float* T, const int32_t* rowptr, const int32_t* src,
                                        const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                                        const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                                        const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                                       float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                                       float* d_msg, uint32_t* signs, float* bias_sums, float* dz_amax, int64_t n_atoms, int64_t n_edges, int32_t heads,
                                        int32_t f, int32_t hd, float eps, void* stream_) {
   return edge_bwd_prep_impl<true>(P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-                                  g_out, d_gate, d_msg, signs, bias_sums, n_atoms, n_edges, heads, f, hd, eps, stream_);
+                                  g_out, d_gate, d_msg, signs, bias_sums, dz_amax, n_atoms, n_edges, heads, f, hd, eps, stream_);
 }

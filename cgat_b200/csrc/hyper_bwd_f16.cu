@@ -1,0 +1,200 @@
+// Hypernetwork linear layer, weight gradient on kind::f16 passes (SURVEY.md §8a row A12 for row A5; VERDICT r01 next #4:
+// "move the gradient-operand kernels to f16x3 with a per-launch power-of-two scale").
+//
+//   dL/dW[o*F+i, k] = sum_n g[n,o] * y[n,i] * z[n,k]           (g = dL/dy_out)
+//
+// Same decomposition as hyper_bwd.cu (one CTA = pair of output channels x atom range; the scaled rows g[n,o]*y[n,:] are
+// formed in registers while they are staged; both operands MN-major, contraction over atoms) with fp16 hi/lo operand
+// pairs instead of tf32 hi/lo pairs: kind::f16 runs at twice the rate for the same operand bytes, a stage is 48 KB
+// instead of 96 KB (four stages instead of two).  The gradient operand needs a range: the rows are multiplied by a
+// power of two s = 2^(4 - ceil(log2 amax|g|)) read from device memory (amax is produced by cgat_hyper_rowscale_f16,
+// which reads the same g just before), so max |g| s = 16 and fp16 has 2^12 of headroom left for |y|; the epilogue
+// divides by s.  Small elements keep an ABSOLUTE error of 2^-25 / s, i.e. 2^-29 of the largest one (tc_common.cuh).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace cgat {
+namespace {
+using namespace tc;
+
+constexpr int kF = 128;
+constexpr int kThreadsW = 128 + 256 + 32;
+constexpr int kRows = 32;                     // atoms (K rows) per stage
+constexpr int kImg = kRows * 128;             // one image: 64 columns x 32 rows of halves = 4 KB
+constexpr int kPart = 2 * kImg;               // 128 columns = 2 images = 8 KB
+constexpr int kStage = 6 * kPart;             // Z hi/lo, A0 hi/lo, A1 hi/lo = 48 KB
+constexpr int kStagesW = 4;
+constexpr int kSmemW = kStagesW * kStage + 256 + 1024;
+
+__global__ void __launch_bounds__(kThreadsW, 1)
+hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ z,
+                       const float* __restrict__ g_amax, float* __restrict__ out, int n_atoms, int n_split) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * kStage);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStagesW;
+  uint64_t* accum = bars + 2 * kStagesW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int pair = blockIdx.x / n_split, split = blockIdx.x % n_split;
+  const int o0 = 2 * pair;
+  const int n_lo = (int)((int64_t)n_atoms * split / n_split), n_hi = (int)((int64_t)n_atoms * (split + 1) / n_split);
+  const int n_chunks = (n_hi - n_lo + kRows - 1) / kRows;
+  // power-of-two scale of the gradient operand: max |g| * s in (8, 16]
+  const float amax = __ldg(g_amax);
+  int ex;
+  frexpf(amax, &ex);                                           // amax = m * 2^ex, m in [0.5, 1)
+  const float s = (amax > 0.f && amax < INFINITY) ? ldexpf(1.f, 4 - ex) : 1.f;
+  const float s_inv = (amax > 0.f && amax < INFINITY) ? ldexpf(1.f, ex - 4) : 1.f;
+
+  if (tid == 0) {
+    for (int st = 0; st < kStagesW; ++st) {
+      mbar_init(&full[st], 256);
+      mbar_init(&empty[st], 1);
+    }
+    mbar_init(accum, 1);
+    mbar_init_fence();
+  }
+  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    const int i = warp * 32 + lane;  // row of the (F x F) block = input channel i
+    mbar_wait(accum, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int oo = 0; oo < 2; ++oo) {
+      float* dst = out + ((int64_t)split * kF * kF + (int64_t)(o0 + oo) * kF + i) * kF;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        float v[32], w[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + oo * 256 + cc * 32, v);
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + oo * 256 + 128 + cc * 32, w);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 r;
+          r.x = n_chunks ? fmaf(w[4 * j], kF16LoInv, v[4 * j]) * s_inv : 0.f;
+          r.y = n_chunks ? fmaf(w[4 * j + 1], kF16LoInv, v[4 * j + 1]) * s_inv : 0.f;
+          r.z = n_chunks ? fmaf(w[4 * j + 2], kF16LoInv, v[4 * j + 2]) * s_inv : 0.f;
+          r.w = n_chunks ? fmaf(w[4 * j + 3], kF16LoInv, v[4 * j + 3]) * s_inv : 0.f;
+          reinterpret_cast<float4*>(dst + cc * 32)[j] = r;
+        }
+      }
+    }
+    tc_fence_before();
+  } else if (warp < 12) {
+    const int pt = tid - 128;
+    // The rows of chunk ch+1 are requested before chunk ch is converted and stored, so the L2 / HBM latency of the
+    // loads overlaps the conversion instead of preceding it (with the MMAs twice as fast as the tf32 form, the
+    // load -> wait -> convert -> store chain of one chunk was longer than the chunk's MMAs).
+    float4 zv[4], yv[4], zn[4], yn[4];
+    float g0[4], g1[4], g0n[4], g1n[4];
+    auto load = [&](int ch, float4* zz, float4* yy, float* ga, float* gb) {
+      const int n0 = n_lo + ch * kRows;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = pt + 256 * j, r = idx >> 5, q = idx & 31;
+        const int n = n0 + r;
+        zz[j] = yy[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        ga[j] = gb[j] = 0.f;
+        if (ch < n_chunks && n < n_hi) {
+          zz[j] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)n * kF) + q);
+          yy[j] = __ldg(reinterpret_cast<const float4*>(y + (int64_t)n * kF) + q);
+          const float2 gg = __ldg(reinterpret_cast<const float2*>(g + (int64_t)n * kF + o0));
+          ga[j] = gg.x * s, gb[j] = gg.y * s;
+        }
+      }
+    };
+    load(0, zv, yv, g0, g1);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int st = ch % kStagesW, u = ch / kStagesW;
+      load(ch + 1, zn, yn, g0n, g1n);
+      mbar_wait(&empty[st], (u + 1) & 1u);
+      uint8_t* sb = smem + st * kStage;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = pt + 256 * j, r = idx >> 5, q = idx & 31;
+        const uint32_t off = (q >> 4) * kImg + mn16_offset(r, q & 15);
+        uint2 hi, lo;
+        split_f16x4s(zv[j], kF16LoScale, hi, lo);
+        *reinterpret_cast<uint2*>(sb + off) = hi;
+        *reinterpret_cast<uint2*>(sb + kPart + off) = lo;
+        float4 a = make_float4(yv[j].x * g0[j], yv[j].y * g0[j], yv[j].z * g0[j], yv[j].w * g0[j]);
+        split_f16x4s(a, kF16LoScale, hi, lo);
+        *reinterpret_cast<uint2*>(sb + 2 * kPart + off) = hi;
+        *reinterpret_cast<uint2*>(sb + 3 * kPart + off) = lo;
+        a = make_float4(yv[j].x * g1[j], yv[j].y * g1[j], yv[j].z * g1[j], yv[j].w * g1[j]);
+        split_f16x4s(a, kF16LoScale, hi, lo);
+        *reinterpret_cast<uint2*>(sb + 4 * kPart + off) = hi;
+        *reinterpret_cast<uint2*>(sb + 5 * kPart + off) = lo;
+      }
+      fence_async_smem();
+      mbar_arrive(&full[st]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) zv[j] = zn[j], yv[j] = yn[j], g0[j] = g0n[j], g1[j] = g1n[j];
+    }
+  } else {
+    constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int st = ch % kStagesW, u = ch / kStagesW;
+      mbar_wait(&full[st], u & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t z_hi = smem_u32(smem + st * kStage), z_lo = z_hi + kPart;
+#pragma unroll
+        for (int oo = 0; oo < 2; ++oo) {
+          const uint32_t a_hi = z_hi + (2 + 2 * oo) * kPart, a_lo = a_hi + kPart;
+          const uint32_t d = tmem + oo * 256;
+#pragma unroll
+          for (int ks = 0; ks < kRows / 16; ++ks) {   // one MMA consumes 16 K-rows = two 1024-byte groups of every image
+            const uint32_t o = ks * 2048;
+            umma_f16(d + 128, umma_desc_mn_sw128_16b(a_lo + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
+                     (ch | ks) != 0);
+            umma_f16(d + 128, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_lo + o, kImg), idesc, 1);
+            umma_f16(d, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
+                     (ch | ks) != 0);
+          }
+        }
+        umma_commit(&empty[st]);
+        if (ch == n_chunks - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+    if (n_chunks == 0 && lane == 0) mbar_arrive(accum);
+  }
+  __syncthreads();
+  if (warp == 12) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+}  // namespace
+}  // namespace cgat
+
+using namespace cgat;
+
+// cgat_hyper_wgrad on kind::f16 passes: same result layout, (cgat_hyper_wgrad_splits(N), F*F, F) partial dL/dW[:F*F].
+// g_amax: device float holding max |g| (written by cgat_hyper_rowscale_f16 with the same g as `scale`).
+extern "C" int cgat_hyper_wgrad_f16(const float* g, const float* y, const float* z, const float* g_amax, float* out,
+                                    int64_t n_atoms, int32_t f, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (f != kF) return fail(-2, "cgat_hyper_wgrad_f16: only F = 128 is instantiated");
+  if (n_atoms >= (1ll << 31) - 64) return fail(-2, "cgat_hyper_wgrad_f16: too many atoms");
+  if (g_amax == nullptr) return fail(-2, "cgat_hyper_wgrad_f16: g_amax is required");
+  if (n_atoms <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(hyper_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW));
+    configured = true;
+  }
+  const int n_split = cgat_hyper_wgrad_splits(n_atoms);
+  hyper_wgrad_f16_kernel<<<(f / 2) * n_split, kThreadsW, kSmemW, stream>>>(g, y, z, g_amax, out, (int)n_atoms, n_split);
+  return check_launch("hyper_wgrad_f16_kernel");
+}

@@ -41,7 +41,8 @@ template <int F, int kMode>
 __global__ void __launch_bounds__(Hyper16Cfg<F>::kThreads, 1)
 hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
                         const float* __restrict__ e_term2, const float* __restrict__ w_bias,
-                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc, int n_slots) {
+                        const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc, int n_slots,
+                        unsigned int* __restrict__ scale_amax) {
   using Cfg = Hyper16Cfg<F>;
   static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
   extern __shared__ uint8_t smem_raw[];
@@ -98,6 +99,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     uint32_t ocount = 0;
     float y[QF];
+    float sc_max = 0.f;   // kMode 1: max |scale| seen by this thread (the gradient operand of the weight-gradient kernel)
     for (int item = item_lo; item < item_hi; ++item) {
       const int tile = item / n_chunks, chunk = item - tile * n_chunks;
       const int n = tile * 128 + row;
@@ -116,6 +118,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
         const int o = chunk * oc + oi;
         const uint32_t b = ocount & 1u;
         const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
+        if (kMode == 1) sc_max = fmaxf(sc_max, fabsf(sc));
         // The bias of the predicted weight row, p[n, o*F + j] = D_o[n, j] + bl[o*F + j], does not depend on the MMAs:
         // its contribution is taken BEFORE waiting for the accumulator (broadcast loads: every thread of a column
         // group reads the same 32 floats), so only tcgen05.ld + two FMAs per element sit behind the barrier.
@@ -195,6 +198,15 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
             for (int j = 0; j < QF / 4; ++j) z4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
       }
+    }
+    if (kMode == 1 && scale_amax != nullptr) {
+      // order-independent (hence deterministic) maximum: non-negative floats compare like their bit patterns
+      sc_max = fmaxf(sc_max, __shfl_xor_sync(0xffffffffu, sc_max, 16));
+      sc_max = fmaxf(sc_max, __shfl_xor_sync(0xffffffffu, sc_max, 8));
+      sc_max = fmaxf(sc_max, __shfl_xor_sync(0xffffffffu, sc_max, 4));
+      sc_max = fmaxf(sc_max, __shfl_xor_sync(0xffffffffu, sc_max, 2));
+      sc_max = fmaxf(sc_max, __shfl_xor_sync(0xffffffffu, sc_max, 1));
+      if (lane == 0 && grp == 0) atomicMax(scale_amax, __float_as_uint(sc_max));
     }
   } else if (warp < kMmaWarp) {
     // ------------------------------------------------------------------ activation-tile stagers + weight TMA
@@ -314,7 +326,8 @@ using namespace cgat;
 namespace {
 template <int kMode>
 int launch_hyper16(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
-                   const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {
+                   const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream,
+                   float* scale_amax = nullptr) {
   using Cfg = Hyper16Cfg<128>;
   if (n_atoms <= 0) return 0;
   if (f != 128) return fail(-2, "cgat_hyper_*_f16: only F = 128 is instantiated");
@@ -329,7 +342,8 @@ int launch_hyper16(const float* z, const float* y_in, const float* e_term, const
   const int oc = hyper_chunk(n_atoms, f);
   const int grid = hyper_grid(n_atoms, f);
   hyper_rowdot_f16_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f));
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f),
+      reinterpret_cast<unsigned int*>(scale_amax));
   return check_launch(kMode == 0 ? "hyper_rowdot_f16_kernel" : "hyper_rowscale_f16_kernel");
 }
 }  // namespace
@@ -345,4 +359,13 @@ extern "C" int cgat_hyper_rowdot_fwd_f16(const float* z, const float* y_in, cons
 extern "C" int cgat_hyper_rowscale_f16(const float* a, const float* scale, const float* w_bias, const float* w_packed,
                                        float* partial, int64_t n_atoms, int32_t f, void* stream_) {
   return launch_hyper16<1>(a, scale, nullptr, nullptr, w_bias, w_packed, partial, n_atoms, f, (cudaStream_t)stream_);
+}
+
+// The same, and additionally scale_amax[0] = max(scale_amax[0], max |scale|) (device float, zero it beforehand): the
+// power-of-two range of the gradient operand that cgat_hyper_wgrad_f16 needs, taken while `scale` is being read anyway.
+extern "C" int cgat_hyper_rowscale_f16_amax(const float* a, const float* scale, const float* w_bias,
+                                            const float* w_packed, float* partial, float* scale_amax, int64_t n_atoms,
+                                            int32_t f, void* stream_) {
+  return launch_hyper16<1>(a, scale, nullptr, nullptr, w_bias, w_packed, partial, n_atoms, f, (cudaStream_t)stream_,
+                           scale_amax);
 }

@@ -333,12 +333,29 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       : "memory");
 }
 // two fp32 -> packed (hi.x | hi.y << 16), (lo.x | lo.y << 16), lo = rn_f16((x - hi) * lo_scale)
+// hi is taken as the fp32 value rounded to 11 significant bits on the bit pattern (round_tf32: fp16 and tf32 carry the
+// same 11 bits), which IS the fp16 value whenever x lies in fp16's normal range, so no half -> float conversion is
+// needed to form the remainder and each pair costs two packed conversions (F2FP) instead of six scalar ones — the
+// split was the largest item of the f16 producers' instruction mix.  Below fp16's normal range (|x| < 2^-14) the
+// packed conversion rounds hi once more and that second rounding (< 2^-25 absolute) is not carried into lo: an absolute
+// error floor far below the fp32 rounding error of the in-range elements it is summed with.  -DCGAT_F16_SPLIT_EXACT
+// restores the conversion-based form.
+__device__ __forceinline__ uint32_t pack_half2_rn(float x, float y) {
+  const __half2 h = __floats2half2_rn(x, y);   // .x = low half
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
 __device__ __forceinline__ void split_f16x2s(float x, float y, float lo_scale, uint32_t& hi, uint32_t& lo) {
+#ifdef CGAT_F16_SPLIT_EXACT
   const __half hx = __float2half_rn(x), hy = __float2half_rn(y);
   const __half lx = __float2half_rn((x - __half2float(hx)) * lo_scale);
   const __half ly = __float2half_rn((y - __half2float(hy)) * lo_scale);
   hi = (uint32_t)__half_as_ushort(hx) | ((uint32_t)__half_as_ushort(hy) << 16);
   lo = (uint32_t)__half_as_ushort(lx) | ((uint32_t)__half_as_ushort(ly) << 16);
+#else
+  const float hx = round_tf32(x), hy = round_tf32(y);
+  hi = pack_half2_rn(hx, hy);
+  lo = pack_half2_rn((x - hx) * lo_scale, (y - hy) * lo_scale);
+#endif
 }
 // 8 consecutive fp32 (two float4) -> one 16-byte chunk of the hi image and one of the lo image
 __device__ __forceinline__ void split_f16x8s(const float4& a, const float4& b, float lo_scale, uint4& hi, uint4& lo) {
@@ -350,6 +367,33 @@ __device__ __forceinline__ void split_f16x8s(const float4& a, const float4& b, f
 // the scaled-lo form used with a separate correction accumulator (hyper_f16.cu)
 __device__ __forceinline__ void split_f16x8(const float4& a, const float4& b, uint4& hi, uint4& lo) {
   split_f16x8s(a, b, kF16LoScale, hi, lo);
+}
+
+// ---- MN-major fp16 operands (contraction over the ROWS of the source: weight-gradient shapes) --------------------
+// Canonical SWIZZLE_128B MN-major layout for 16-bit elements (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>:
+// Swizzle<3,4,3> o ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units): an "image" holds the K rows of one block of 64
+// consecutive M/N elements, 128 bytes per row; 8-row groups (1024 B) are SBO apart, images LBO apart; inside a group
+// the 16-byte unit u of row r sits at unit (u ^ (r & 7)) — physically the same pattern as the K-major SW128 tile.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128_16b(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;       // next block of 64 M/N elements
+  d |= (uint64_t)(kSwizzleAtomBytes >> 4) << 32;          // next group of 8 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                                 // SWIZZLE_128B
+  return d;
+}
+// byte offset inside an image of the 8-byte half-unit that holds M/N elements [4*q4, 4*q4 + 4) (q4 in 0..15) of K row r
+__device__ __forceinline__ uint32_t mn16_offset(uint32_t r, uint32_t q4) {
+  return (r >> 3) * kSwizzleAtomBytes + (r & 7u) * kSwizzleRowBytes + ((((q4 >> 1) ^ (r & 7u)) << 4) | ((q4 & 1u) << 3));
+}
+__host__ __device__ constexpr uint32_t umma_idesc_f16_mn(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 15) | (1u << 16) | ((n >> 3) << 17) | ((m >> 4) << 24);   // F32 accumulate, A and B MN-major
+}
+// four fp32 -> four fp16 hi halves + four fp16 lo halves (lo = rn_f16((x - hi) * lo_scale)), 8 bytes each
+__device__ __forceinline__ void split_f16x4s(const float4& a, float lo_scale, uint2& hi, uint2& lo) {
+  split_f16x2s(a.x, a.y, lo_scale, hi.x, lo.x);
+  split_f16x2s(a.z, a.w, lo_scale, hi.y, lo.y);
 }
 
 // Packed K-major fp16 operand: tiles of kPackRows rows x kPackChunk16 halves (128-byte rows, SWIZZLE_128B), stored

@@ -83,6 +83,8 @@ _TRUNK = os.environ.get("CGAT_B200_TRUNK", "1") != "0"   # hypernetwork trunks: 
 # activation x weight tensor-core kernels on kind::f16 with scaled fp16 hi/lo operands (1) or kind::tf32 hi/lo (0)
 _F16X3 = os.environ.get("CGAT_B200_F16X3", "1") != "0"
 _F16X3_EDGE = os.environ.get("CGAT_B200_F16X3_EDGE", "1") != "0"   # the same for the edge-attention forward / bwd_prep
+# gradient-operand kernels (hyper weight gradient) on kind::f16 with a per-launch power-of-two scale (1) or kind::tf32 (0)
+_F16X3_GRAD = os.environ.get("CGAT_B200_F16X3_GRAD", "1") != "0"
 _EDGE_W2_PRESCALE = 64.0   # cgat_edge_attn_*_f16 expect W2 packed as f16(w * 2^6) hi/lo with an unscaled lo
 # EXPERIMENTAL, off by default (not yet measured on the GPU): the small MLPs around the fused kernels (Roost, crystal
 # pool, output network, edge table) on the 3-pass tensor-core GEMMs instead of the library's SIMT sgemm kernels
@@ -391,8 +393,15 @@ class _HyperLinear(torch.autograd.Function):
         # dL/dy[n,i] = sum_o g[n,o] (W z[n] + b)[o*F+i]: recomputed tile by tile on the tensor cores
         bias = bias.contiguous()
         buf = torch.empty((parts, n, f), dtype=torch.float32, device=y.device)
-        _lib.call(rowscale, _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed), _lib.ptr(buf),
-                  n, f, _lib.stream(), work=work)
+        f16_grad = ctx.f16 and _F16X3_GRAD
+        if f16_grad:
+            # the same launch also leaves max |g| in device memory: the range of cgat_hyper_wgrad_f16's gradient operand
+            g_amax = torch.zeros(1, dtype=torch.float32, device=y.device)
+            _lib.call("cgat_hyper_rowscale_f16_amax", _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed),
+                      _lib.ptr(buf), _lib.ptr(g_amax), n, f, _lib.stream(), work=work)
+        else:
+            _lib.call(rowscale, _lib.ptr(z), _lib.ptr(g), _lib.ptr(bias), _lib.ptr(w_packed), _lib.ptr(buf),
+                      n, f, _lib.stream(), work=work)
         g_y = sum_parts(buf)
         # dL/dz[n,k] = sum_o g[n,o] sum_i y[n,i] W[o*F+i,k] (+ the bias-tail rows unless they went through `e`)
         buf2 = torch.empty_like(buf)
@@ -405,9 +414,15 @@ class _HyperLinear(torch.autograd.Function):
         lib = _lib.load()
         splits = int(lib.cgat_hyper_wgrad_splits(n))
         wpart = torch.empty((splits, ff, f), dtype=torch.float32, device=y.device)
-        _lib.call("cgat_hyper_wgrad", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(wpart), n, f, _lib.stream(),
-                  work=dict(key="hyper_wgrad", bound="tensor", flops=2.0 * n * f * ff,
-                            note="3xTF32: 3 tensor passes per algorithmic flop"))
+        if f16_grad:
+            _lib.call("cgat_hyper_wgrad_f16", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(g_amax), _lib.ptr(wpart),
+                      n, f, _lib.stream(),
+                      work=dict(key="hyper_wgrad", bound="tensor", flops=2.0 * n * f * ff,
+                                note="f16x3: 3 kind::f16 passes per algorithmic flop, gradient operand scaled by 2^k"))
+        else:
+            _lib.call("cgat_hyper_wgrad", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(wpart), n, f, _lib.stream(),
+                      work=dict(key="hyper_wgrad", bound="tensor", flops=2.0 * n * f * ff,
+                                note="3xTF32: 3 tensor passes per algorithmic flop"))
         g_w = torch.empty_like(weight)
         sum_parts(wpart, out=g_w[:ff])
         yz = torch.cat([y, z], dim=1)                      # bias-shaped rows: g^T [y | z]
@@ -655,11 +670,14 @@ class _EdgeAttentionFused(torch.autograd.Function):
         # per-CTA column sums of d_msg | d_gate (the second-layer bias gradients) come out of the same kernel
         bsum = (torch.empty if e > 0 else torch.zeros)((int(lib.cgat_edge_attn_grid(e)), 2, heads, f),
                                                       dtype=torch.float32, device=dev)   # e == 0: no launch, no writes
+        # max |dL/da|, |dL/dv| (device float, zeroed by the kernel's wrapper): the range of the f16 weight-gradient operand
+        f16_grad = _F16X3_GRAD and hd % 16 == 0 and hd <= 256
+        dz_amax = torch.empty(1, dtype=torch.float32, device=dev) if f16_grad else None
         _lib.call("cgat_edge_attn_bwd_prep_f16" if ctx.f16 else "cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T),
                   _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed), _lib.ptr(b2a),
                   _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(g), _lib.ptr(d_gate),
-                  _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(bsum), n, e, heads, f, hd, 1e-16, st,
+                  _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(bsum), _lib.ptr(dz_amax), n, e, heads, f, hd, 1e-16, st,
                   work=dict(key="edge_attn_bwd_prep", bound="tensor", flops=flops2))
         # 2. dgrad on the tensor cores -> per-edge d_pre, then its per-destination / per-source / per-rank sums
         #    (HBM-bound, cgat_edge_attn_reduce)
@@ -685,9 +703,15 @@ class _EdgeAttentionFused(torch.autograd.Function):
         # 3. second-layer weight / bias gradients
         splits = int(lib.cgat_edge_attn_wgrad_splits(heads))
         part = torch.empty((splits, 2, heads, f, hd), dtype=torch.float32, device=dev)
-        _lib.call("cgat_edge_attn_wgrad", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
-                  _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(part), e, heads, f, hd, st,
-                  work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2))
+        if f16_grad:
+            _lib.call("cgat_edge_attn_wgrad_f16", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
+                      _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(dz_amax), _lib.ptr(part), e, heads,
+                      f, hd, st, work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2,
+                                           note="f16x3, gradient operand scaled by 2^k"))
+        else:
+            _lib.call("cgat_edge_attn_wgrad", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
+                      _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(part), e, heads, f, hd, st,
+                      work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2))
         d_w2 = sum_parts(part)
         g_w2a, g_w2m = d_w2[0].reshape(w2a.shape), d_w2[1].reshape(w2m.shape)
         g_b2 = sum_parts(bsum)

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CGAT_B200_ABI_VERSION 3 /* 2: cgat_edge_attn_bwd_prep gained bias_sums; f16 entry points. 3: train-step glue */
+#define CGAT_B200_ABI_VERSION 4 /* 2: bwd_prep gained bias_sums; f16 entry points. 3: train-step glue. 4: bwd_prep gained dz_amax */
 
 int cgat_abi_version(void);
 const char* cgat_last_error(void);
@@ -197,6 +197,14 @@ int32_t cgat_hyper_wgrad_splits(int64_t n_atoms);
 int cgat_hyper_wgrad(const float* g, const float* y, const float* z, float* out, int64_t n_atoms, int32_t f,
                      void* stream);
 
+/* kind::f16 form of cgat_hyper_wgrad (twice the tensor rate; 48 KB stages): the gradient operand g is multiplied by a
+ * power of two derived from g_amax[0] = max |g| (device float), which cgat_hyper_rowscale_f16_amax produces while it
+ * reads the same g as `scale` (scale_amax must be zeroed before the launch).                              */
+int cgat_hyper_rowscale_f16_amax(const float* a, const float* scale, const float* w_bias, const float* w_packed,
+                                 float* partial, float* scale_amax, int64_t n_atoms, int32_t f, void* stream);
+int cgat_hyper_wgrad_f16(const float* g, const float* y, const float* z, const float* g_amax, float* out,
+                         int64_t n_atoms, int32_t f, void* stream);
+
 /* ---- fused edge attention, backward -------------------------------------
  * Step 1: recompute a, v; write d_gate = dL/da, d_msg = dL/dv (E,H,F; destination-sorted rows) and the
  *         LeakyReLU sign masks signs[2][H][ceil(Hd/32)][E].  g_out = dL/d out (N,H,F).
@@ -212,9 +220,11 @@ int cgat_edge_attn_bwd_prep(const float* P, const float* T, const int32_t* rowpt
                             const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                             const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                             const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                            float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
-                            int32_t f, int32_t hd, float eps, void* stream);
-/* bias_sums (optional): (cgat_edge_attn_grid(E), 2, H, F) per-CTA column sums of d_msg | d_gate; their sum over
+                            float* d_msg, uint32_t* signs, float* bias_sums, float* dz_amax, int64_t n_atoms,
+                            int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps, void* stream);
+/* dz_amax (optional, device float): receives max |d_gate|, |d_msg| — the power-of-two range that the kind::f16
+ * weight-gradient kernel (cgat_edge_attn_wgrad_f16) applies to its gradient operand.
+ * bias_sums (optional): (cgat_edge_attn_grid(E), 2, H, F) per-CTA column sums of d_msg | d_gate; their sum over
  * dim 0 is dL/d b2 of the message | gate net, so the caller never re-reads the (E, H, F) tensors for it.       */
 int32_t cgat_edge_attn_grid(int64_t n_edges);
 /* kind::f16 form of cgat_edge_attn_bwd_prep (w2*_packed as for cgat_edge_attn_fwd_f16). */
@@ -222,8 +232,8 @@ int cgat_edge_attn_bwd_prep_f16(const float* P, const float* T, const int32_t* r
                             const int32_t* dst, const int32_t* rank, const float* w2a_packed,
                             const float* w2m_packed, const float* b2a, const float* b2m, const float* out,
                             const float* seg_max, const float* seg_den, const float* g_out, float* d_gate,
-                            float* d_msg, uint32_t* signs, float* bias_sums, int64_t n_atoms, int64_t n_edges, int32_t heads,
-                            int32_t f, int32_t hd, float eps, void* stream);
+                            float* d_msg, uint32_t* signs, float* bias_sums, float* dz_amax, int64_t n_atoms,
+                            int64_t n_edges, int32_t heads, int32_t f, int32_t hd, float eps, void* stream);
 int32_t cgat_edge_attn_dgrad_grid(int64_t n_edges);
 int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t* signs, const int32_t* segptr,
                          const int32_t* seg, const int32_t* row, const int32_t* rnk, const float* wt_a_packed,
@@ -245,6 +255,11 @@ int32_t cgat_edge_attn_wgrad_splits(int32_t heads);
 int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
                          const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
                          int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream);
+/* kind::f16 form (twice the tensor rate, 4 x 48 KB stages, two alternating producer groups): d_gate / d_msg are
+ * multiplied by a power of two derived from dz_amax[0] (left by cgat_edge_attn_bwd_prep) and the result divided by it. */
+int cgat_edge_attn_wgrad_f16(const float* P, const float* T, const int32_t* src, const int32_t* dst,
+                             const int32_t* rank, const float* d_gate, const float* d_msg, const float* dz_amax,
+                             float* out, int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream);
 
 /* ---- train-step glue ----------------------------------------------------------
  * cgat_sum_parts: out[i] = (accumulate ? out[i] : 0) + sum_{p < n_parts} parts[p * part_stride + i], parts added in
