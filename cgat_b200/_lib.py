@@ -65,6 +65,7 @@ SIGNATURES = {
     "cgat_edge_attn_grid": (_I32, [_I64]),
     "cgat_edge_attn_dgrad_grid": (_I32, [_I64]),
     "cgat_edge_attn_dgrad": (ctypes.c_int, [_P] * 10 + [_I64, _I32, _P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P]),
+    "cgat_edge_attn_dgrad_f16": (ctypes.c_int, [_P] * 9 + [_I64, _I64, _I32, _I32, _I32, _P]),
     "cgat_edge_attn_reduce_chunks": (_I32, [_I64]),
     "cgat_edge_attn_reduce": (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I32, _I64, _I32, _P]),
     "cgat_edge_attn_wgrad_splits": (_I32, [_I32]),

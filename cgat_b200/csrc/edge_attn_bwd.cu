@@ -46,6 +46,7 @@ struct DgradArgs {
   float* G;                // (N, ldg); this pass writes columns [col_off, col_off + 2*H*Hd)
   float* d_rank;           // (grid, n_ranks, 2*H*Hd) partial dL/dT per CTA, or null
   float* d_pre;            // (E, 2*H*Hd) per-edge pre-activation gradients in THIS edge order, or null
+  const float* dz_amax;    // kF16: device float max |d_gate|, |d_msg| (power-of-two range of the gradient operand)
   int64_t ldg;
   int col_off, n_atoms, n_edges, heads, hd, n_ranks;
 };
@@ -62,6 +63,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
+// kF16: both MMA operands as fp16 hi/lo pairs on kind::f16 (twice the tensor rate, half the W2^T stream from L2): W2^T
+// packed by cgat_pack_kmajor_f16 (lo scaled by 2^11, separate correction accumulator as in hyper_f16.cu), the gradient
+// operand dZ multiplied by a power of two s = 2^(4 - ceil(log2 amax)) while it is staged; the epilogue multiplies by 1/s.
+template <bool kF16>
 __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -81,7 +86,16 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
   const int kcn = (hd + 31) / 32;       // sign words per (net, head, edge)
   const int nhalf = (hd + 127) / 128;   // M tiles of 128 hidden units per head
   const int n_items = 2 * H * nhalf;
-  constexpr int kcf = kBF / 32;         // K chunks of the dgrad contraction (over channels)
+  constexpr int kChunkF = kF16 ? kPackChunk16 : kPackChunk;   // channels per pipeline stage
+  constexpr int kcf = kBF / kChunkF;    // K chunks of the dgrad contraction (over channels)
+  float s_scale = 1.f, s_inv = 1.f;
+  if (kF16) {
+    const float amax = __ldg(g.dz_amax);
+    int ex;
+    frexpf(amax, &ex);
+    if (amax > 0.f && amax < INFINITY) s_scale = ldexpf(1.f, 4 - ex), s_inv = ldexpf(1.f, ex - 4);
+  }
+  const float corr = kF16 ? kF16LoInv : 1.f;   // the correction accumulator of the f16 form carries lo * 2^11
 
   if (tid == 0) {
     for (int s = 0; s < kBStages; ++s) {
@@ -159,7 +173,7 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
             const int left = kvalid ? nv - cc * 32 : 0;  // columns of this group that are real edges
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
-              const float dp = (v[j] + w[j]) * (((wd[j] >> bitpos) & 1u) ? 1.f : 0.01f);
+              const float dp = fmaf(w[j], corr, v[j]) * (((wd[j] >> bitpos) & 1u) ? s_inv : 0.01f * s_inv);
               if (j < left) *prow = dp;
               prow += ldd;
             }
@@ -299,6 +313,48 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
         }
         // the dZ rows of K chunk kc+1 are requested before this thread waits for the stage of chunk kc, so the
         // L2 / HBM latency of the loads overlaps the wait and the conversion (was: load -> wait for data -> convert)
+        if constexpr (kF16) {
+          // slot = (edge row, 16-byte chunk) = 8 consecutive channels: two float4 per slot, 4 slots per thread
+          float4 xa[4], xb[4], na[4], nb[4];
+          auto load = [&](int kc, float4* aa, float4* bb) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int cch = (pt + kBProducers * j) & 7;
+              aa[j] = bb[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (kc < kcf && rowoff[j] >= 0) {
+                const float4* p = reinterpret_cast<const float4*>(dz[net] + rowoff[j] + kc * kChunkF + cch * 8);
+                aa[j] = __ldg(p), bb[j] = __ldg(p + 1);
+              }
+            }
+          };
+          load(0, xa, xb);
+          for (int kc = 0; kc < kcf; ++kc, ++cnt) {
+            const uint32_t s = cnt % kBStages, u = cnt / kBStages;
+            load(kc + 1, na, nb);
+            mbar_wait(&empty[s], (u + 1) & 1u);
+            uint8_t* st = stages + s * kBStageBytes;
+            if (pt == 0) {
+              mbar_expect_tx(&full[s], kPackStageBytes);
+              bulk_g2s(st, wt[net] + ((int64_t)(h * nhalf + half) * kcf + kc) * kPackStageBytes, kPackStageBytes, &full[s]);
+            }
+            uint8_t* bh = st + kPackStageBytes;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int idx = pt + kBProducers * j;
+              const float4 a = make_float4(xa[j].x * s_scale, xa[j].y * s_scale, xa[j].z * s_scale, xa[j].w * s_scale);
+              const float4 b = make_float4(xb[j].x * s_scale, xb[j].y * s_scale, xb[j].z * s_scale, xb[j].w * s_scale);
+              uint4 hi, lo;
+              split_f16x8(a, b, hi, lo);
+              const uint32_t off = sw128_offset(idx >> 3, idx & 7);
+              *reinterpret_cast<uint4*>(bh + off) = hi;
+              *reinterpret_cast<uint4*>(bh + kPackImageBytes + off) = lo;
+            }
+            fence_async_smem();
+            mbar_arrive(&full[s]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) xa[j] = na[j], xb[j] = nb[j];
+          }
+        } else {
         float4 x[4], nx[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -336,11 +392,12 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
 #pragma unroll
           for (int j = 0; j < 4; ++j) x[j] = nx[j];
         }
+        }
       }
     }
   } else {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = umma_idesc_tf32(128, kBT);
+    constexpr uint32_t idesc = kF16 ? umma_idesc_f16(128, kBT) : umma_idesc_tf32(128, kBT);
     uint32_t cnt = 0, icount = 0;
     for (int item = 0; item < n_items; ++item) {
       for (int tile = 0; tile < n_tiles; ++tile, ++icount) {
@@ -358,9 +415,15 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
-              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-              umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              if constexpr (kF16) {
+                umma_f16(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                umma_f16(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              } else {
+                umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              }
             }
             umma_commit(&empty[s]);
             if (kc == kcf - 1) umma_commit(&tmem_full[b]);
@@ -696,14 +759,38 @@ extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, con
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     configured = true;
   }
   if (d_pre && row) return fail(-2, "cgat_edge_attn_dgrad: d_pre needs the identity edge order (row == NULL)");
-  DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, d_pre, ldg,
+  DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, d_pre, nullptr, ldg,
               col_off, (int)n_atoms, (int)n_edges, heads, hd, n_ranks};
-  edge_dgrad_kernel<<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
+  edge_dgrad_kernel<false><<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
   return check_launch("edge_dgrad_kernel");
+}
+
+// kind::f16 form of the d_pre variant (identity edge order): wt_*_packed = cgat_pack_kmajor_f16 of W2^T per head,
+// dz_amax = the device float cgat_edge_attn_bwd_prep left (max |d_gate|, |d_msg|).  Writes d_pre (E, 2*H*Hd).
+extern "C" int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg, const uint32_t* signs,
+                                        const int32_t* segptr, const int32_t* seg, const float* wt_a_packed,
+                                        const float* wt_m_packed, const float* dz_amax, float* d_pre, int64_t n_atoms,
+                                        int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (f != kBF) return fail(-2, "cgat_edge_attn_dgrad_f16: only F = 128 is instantiated");
+  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 127))
+    return fail(-2, "cgat_edge_attn_dgrad_f16: heads must be in [1,8] and the hidden width a multiple of 128");
+  if (!d_pre || !dz_amax) return fail(-2, "cgat_edge_attn_dgrad_f16: d_pre and dz_amax are required");
+  if (n_atoms <= 0 || n_edges <= 0) return 0;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    configured = true;
+  }
+  DgradArgs a{d_gate, d_msg, signs, segptr, seg, nullptr, nullptr, wt_a_packed, wt_m_packed, nullptr, nullptr, d_pre,
+              dz_amax, 0, 0, (int)n_atoms, (int)n_edges, heads, hd, 1};
+  edge_dgrad_kernel<true><<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
+  return check_launch("edge_dgrad_f16_kernel");
 }
 
 extern "C" int32_t cgat_edge_attn_wgrad_splits(int32_t heads) {

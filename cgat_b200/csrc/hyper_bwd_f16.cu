@@ -18,7 +18,8 @@ namespace {
 using namespace tc;
 
 constexpr int kF = 128;
-constexpr int kThreadsW = 128 + 256 + 32;
+constexpr int kThreadsW = 128 + 512 + 32;
+constexpr int kMmaWarpW = (128 + 512) / 32;
 constexpr int kRows = 32;                     // atoms (K rows) per stage
 constexpr int kImg = kRows * 128;             // one image: 64 columns x 32 rows of halves = 4 KB
 constexpr int kPart = 2 * kImg;               // 128 columns = 2 images = 8 KB
@@ -57,7 +58,7 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
     mbar_init(accum, 1);
     mbar_init_fence();
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == kMmaWarpW) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -88,38 +89,34 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
       }
     }
     tc_fence_before();
-  } else if (warp < 12) {
-    const int pt = tid - 128;
-    // The rows of chunk ch+1 are requested before chunk ch is converted and stored, so the L2 / HBM latency of the
-    // loads overlaps the conversion instead of preceding it (with the MMAs twice as fast as the tf32 form, the
-    // load -> wait -> convert -> store chain of one chunk was longer than the chunk's MMAs).
-    float4 zv[4], yv[4], zn[4], yn[4];
-    float g0[4], g1[4], g0n[4], g1n[4];
-    auto load = [&](int ch, float4* zz, float4* yy, float* ga, float* gb) {
+  } else if (warp < kMmaWarpW) {
+    // 16 producer warps in two groups that take alternate chunks: with the MMAs twice as fast as the tf32 form the
+    // conversion work of 8 warps (two per scheduler, dependent ALU chains) was pacing the kernel, and a software
+    // prefetch of the next chunk's rows changed nothing (measured) — it is issue slots / latency hiding, not loads.
+    const int pt = tid - 128, grp = pt >> 8, pl = pt & 255;
+    for (int ch = grp; ch < n_chunks; ch += 2) {
+      const int st = ch % kStagesW, u = ch / kStagesW;
       const int n0 = n_lo + ch * kRows;
+      float4 zv[4], yv[4];
+      float g0[4], g1[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int idx = pt + 256 * j, r = idx >> 5, q = idx & 31;
+        const int idx = pl + 256 * j, r = idx >> 5, q = idx & 31;
         const int n = n0 + r;
-        zz[j] = yy[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        ga[j] = gb[j] = 0.f;
-        if (ch < n_chunks && n < n_hi) {
-          zz[j] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)n * kF) + q);
-          yy[j] = __ldg(reinterpret_cast<const float4*>(y + (int64_t)n * kF) + q);
+        zv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        g0[j] = g1[j] = 0.f;
+        if (n < n_hi) {
+          zv[j] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)n * kF) + q);
+          yv[j] = __ldg(reinterpret_cast<const float4*>(y + (int64_t)n * kF) + q);
           const float2 gg = __ldg(reinterpret_cast<const float2*>(g + (int64_t)n * kF + o0));
-          ga[j] = gg.x * s, gb[j] = gg.y * s;
+          g0[j] = gg.x * s, g1[j] = gg.y * s;
         }
       }
-    };
-    load(0, zv, yv, g0, g1);
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      const int st = ch % kStagesW, u = ch / kStagesW;
-      load(ch + 1, zn, yn, g0n, g1n);
       mbar_wait(&empty[st], (u + 1) & 1u);
       uint8_t* sb = smem + st * kStage;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const int idx = pt + 256 * j, r = idx >> 5, q = idx & 31;
+        const int idx = pl + 256 * j, r = idx >> 5, q = idx & 31;
         const uint32_t off = (q >> 4) * kImg + mn16_offset(r, q & 15);
         uint2 hi, lo;
         split_f16x4s(zv[j], kF16LoScale, hi, lo);
@@ -136,8 +133,6 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
       }
       fence_async_smem();
       mbar_arrive(&full[st]);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) zv[j] = zn[j], yv[j] = yn[j], g0[j] = g0n[j], g1[j] = g1n[j];
     }
   } else {
     constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128);
@@ -169,7 +164,7 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
     if (n_chunks == 0 && lane == 0) mbar_arrive(accum);
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kMmaWarpW) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }

@@ -572,16 +572,18 @@ def hyper_trunks(h, layers, tails):
     return list(Z.unbind(0)), list(E.unbind(0))
 
 
-def _w2_transposed_packed(w2, heads):
-    """Packed W2^T per head, (H*Hd, F): row h*Hd+k, col c = W2[h*F+c, k] — the A operand of the dgrad MMAs."""
+def _w2_transposed_packed(w2, heads, f16=False):
+    """Packed W2^T per head, (H*Hd, F): row h*Hd+k, col c = W2[h*F+c, k] — the A operand of the dgrad MMAs
+    (tf32 hi/lo images, or fp16 hi / 2^11-scaled lo images for cgat_edge_attn_dgrad_f16)."""
     cache = w2.__dict__.setdefault("_cgat_packed", {})
-    hit = cache.get("w2t")
+    tag = "w2t16" if f16 else "w2t"
+    hit = cache.get(tag)
     if hit is not None and hit[0] == (w2._version, _pack_epoch) and hit[2] == w2.data_ptr():
         return hit[1]
     hf, hd = w2.shape[0], w2.shape[1]
     wt = w2.detach().view(heads, hf // heads, hd).transpose(1, 2).reshape(heads * hd, hf // heads).contiguous()
-    buf = packed_kmajor(wt)   # wt is a temporary: its packed image is a fresh buffer owned by this cache entry
-    cache["w2t"] = ((w2._version, _pack_epoch), buf, w2.data_ptr())
+    buf = packed_kmajor(wt, f16=f16)   # wt is a temporary: its packed image is a fresh buffer owned by this cache entry
+    cache[tag] = ((w2._version, _pack_epoch), buf, w2.data_ptr())
     return buf
 
 
@@ -671,7 +673,7 @@ class _EdgeAttentionFused(torch.autograd.Function):
         bsum = (torch.empty if e > 0 else torch.zeros)((int(lib.cgat_edge_attn_grid(e)), 2, heads, f),
                                                       dtype=torch.float32, device=dev)   # e == 0: no launch, no writes
         # max |dL/da|, |dL/dv| (device float, zeroed by the kernel's wrapper): the range of the f16 weight-gradient operand
-        f16_grad = _F16X3_GRAD and hd % 16 == 0 and hd <= 256
+        f16_grad = _F16X3_GRAD and hd % 128 == 0 and hd <= 256
         dz_amax = torch.empty(1, dtype=torch.float32, device=dev) if f16_grad else None
         _lib.call("cgat_edge_attn_bwd_prep_f16" if ctx.f16 else "cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T),
                   _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
@@ -681,13 +683,20 @@ class _EdgeAttentionFused(torch.autograd.Function):
                   work=dict(key="edge_attn_bwd_prep", bound="tensor", flops=flops2))
         # 2. dgrad on the tensor cores -> per-edge d_pre, then its per-destination / per-source / per-rank sums
         #    (HBM-bound, cgat_edge_attn_reduce)
-        wt_a, wt_m = _w2_transposed_packed(w2a, heads), _w2_transposed_packed(w2m, heads)
+        wt_a, wt_m = _w2_transposed_packed(w2a, heads, f16_grad), _w2_transposed_packed(w2m, heads, f16_grad)
         n_ranks = tab.shape[0]
         d_pre = torch.empty((e, 2 * hhd), dtype=torch.float32, device=dev)
-        _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(plan.rowptr),
-                  _lib.ptr(plan.dst), None, None, _lib.ptr(wt_a), _lib.ptr(wt_m), None, 4 * hhd, 0, None,
-                  n_ranks, _lib.ptr(d_pre), n, e, heads, f, hd, st,
-                  work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2))
+        if f16_grad:
+            _lib.call("cgat_edge_attn_dgrad_f16", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs),
+                      _lib.ptr(plan.rowptr), _lib.ptr(plan.dst), _lib.ptr(wt_a), _lib.ptr(wt_m), _lib.ptr(dz_amax),
+                      _lib.ptr(d_pre), n, e, heads, f, hd, st,
+                      work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2,
+                                note="f16x3, gradient operand scaled by 2^k"))
+        else:
+            _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(plan.rowptr),
+                      _lib.ptr(plan.dst), None, None, _lib.ptr(wt_a), _lib.ptr(wt_m), None, 4 * hhd, 0, None,
+                      n_ranks, _lib.ptr(d_pre), n, e, heads, f, hd, st,
+                      work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2))
         so = plan.by_source()
         chunks = int(lib.cgat_edge_attn_reduce_chunks(n))
         d_p = torch.empty((n, 4 * hhd), dtype=torch.float32, device=dev)

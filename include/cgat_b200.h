@@ -240,6 +240,13 @@ int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, const uint32_t
                          const float* wt_m_packed, float* G, int64_t ldg, int32_t col_off, float* d_rank,
                          int32_t n_ranks, float* d_pre, int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f,
                          int32_t hd, void* stream);
+/* kind::f16 form of the d_pre variant of cgat_edge_attn_dgrad (identity edge order): wt_*_packed =
+ * cgat_pack_kmajor_f16 of W2^T per head; the gradient operand is scaled by a power of two derived from dz_amax[0]
+ * (left by cgat_edge_attn_bwd_prep).  Writes d_pre (E, 2*H*Hd).                                               */
+int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg, const uint32_t* signs, const int32_t* segptr,
+                             const int32_t* seg, const float* wt_a_packed, const float* wt_m_packed,
+                             const float* dz_amax, float* d_pre, int64_t n_atoms, int64_t n_edges, int32_t heads,
+                             int32_t f, int32_t hd, void* stream);
 /* Segment sums of the per-edge pre-activation gradients d_pre (E, cols; destination-sorted rows) written by
  * cgat_edge_attn_dgrad(d_pre != NULL): HBM-bound, deterministic, replaces the segment sums of the dgrad epilogue
  * and a second tensor-core pass over source-grouped edges.
