@@ -156,7 +156,7 @@ def run_ours(args):
 
     runner = None
     if use_graph:
-        runner = (graphed.GraphedTrainStep(model, opt, crit, sync, graph_collectives=not args.no_graph_collectives)
+        runner = (graphed.GraphedTrainStep(model, opt, crit, sync, graph_collectives=args.graph_collectives)
                   if train else graphed.GraphedForward(model))
 
     def run(sb, tgt):
@@ -235,7 +235,7 @@ def run_ours(args):
         graph_cfg = {"captures": runner.captures, "buckets_atoms_elems_pairs": list(batching.DEFAULT_BUCKETS),
                      "padded_atoms": int(sum(sb.graph.x.shape[0] for sb in pool) / len(pool)),
                      "note": "one whole-step graph per shape bucket (forward, loss, backward, AdamW; on >1 rank the NCCL "
-                             "all-reduces are captured too, one per gradient bucket, overlapping backward); "
+                             "all-reduce and AdamW follow the graph eagerly unless --graph-collectives); "
                              "batches padded with one dummy crystal; throughput counts real crystals only"}
     line = {
         "metric": "crystals/sec " + ("train step (fwd+bwd+AdamW)" if train else "forward (no_grad)"),
@@ -546,8 +546,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg2_train", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-graph-collectives", action="store_true", help="several ranks: keep the NCCL all-reduce and "
-                    "the optimizer outside the captured graph (one blocking all-reduce after backward)")
+    ap.add_argument("--graph-collectives", action="store_true", help="several ranks: capture the bucketed NCCL "
+                    "all-reduces (launched from autograd hooks, overlapping backward) and the optimizer in the step graph. "
+                    "Default: the graph ends after the gradients are packed; one all-reduce + AdamW follow eagerly — "
+                    "measured FASTER on 2 B200s (26.15 vs 26.33 ms): the overlapped NCCL kernels take SMs from the "
+                    "persistent one-CTA-per-SM kernels, which then need a second wave")
     ap.add_argument("--no-forward-record", action="store_true", help="skip the cfg3 forward sub-record")
     ap.add_argument("--no-graph", action="store_true", help="enqueue every kernel from Python instead of replaying "
                     "one captured CUDA graph per shape bucket")
