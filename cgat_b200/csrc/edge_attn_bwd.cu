@@ -23,7 +23,10 @@ using namespace tc;
 constexpr int kBT = 128;  // edges per tile
 constexpr int kBF = 128;  // channels per head (instantiated for F = 128)
 constexpr int kBProducers = 256;
-constexpr int kBThreads = 128 + kBProducers + 32;
+constexpr int kBThreads = 128 + kBProducers + 32;            // wgrad (tf32): 4 epilogue + 8 producer + 1 MMA warps
+constexpr int kDEpilogue = 256;                                // dgrad: two epilogue groups of 4 warps, one per TMEM buffer
+constexpr int kDThreads = kDEpilogue + kBProducers + 32;
+constexpr int kDMmaWarp = (kDEpilogue + kBProducers) / 32;
 constexpr int kBStages = 3;
 constexpr int kBStageBytes = 2 * (int)kPackStageBytes;
 constexpr int kBMetaBufs = 4;
@@ -66,8 +69,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 // kF16: both MMA operands as fp16 hi/lo pairs on kind::f16 (twice the tensor rate, half the W2^T stream from L2): W2^T
 // packed by cgat_pack_kmajor_f16 (lo scaled by 2^11, separate correction accumulator as in hyper_f16.cu), the gradient
 // operand dZ multiplied by a power of two s = 2^(4 - ceil(log2 amax)) while it is staged; the epilogue multiplies by 1/s.
-template <bool kF16>
-__global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArgs g) {
+template <bool kF16, bool kLean>
+__global__ void __launch_bounds__(kDThreads, 1) edge_dgrad_kernel(const DgradArgs g) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
@@ -114,7 +117,7 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
     range[0] = g.segptr[a_lo];
     range[1] = g.segptr[a_hi];
   }
-  if (warp == 12) tmem_alloc(tmem_slot, 512);
+  if (warp == kDMmaWarp) tmem_alloc(tmem_slot, 512);
   if (tid < 128)
     for (int r = 0; r < kBMaxRanks; ++r) rank_acc[r * 128 + tid] = 0.f;
   tc_fence_before();
@@ -124,15 +127,20 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
   const int e_lo = range[0], e_hi = range[1];
   const int n_tiles = (e_hi - e_lo + kBT - 1) / kBT;
 
-  if (warp < 4) {
+  if (warp < kDEpilogue / 32) {
     // ---------------------------------------------------------------- epilogue
+    // Two groups of four warps (a warp reads the TMEM lanes 32*(warp%4)...): in the d_pre form group g owns TMEM
+    // buffer g, i.e. every other (item, tile) — with the MMAs on kind::f16 four warps (one per scheduler, no latency
+    // hiding) were what the kernel waited for.  The segment-sum form carries state across tiles: group 0 runs it alone.
+    const int grp = warp >> 2;
+    const int warp = (threadIdx.x >> 5) & 3;   // lane quadrant from here on
     // Thread = hidden unit (TMEM lane).  Per edge column: one FADD for hi+lo, a select for the LeakyReLU slope and
     // one FADD into the running segment sum; segment / rank-run boundaries come as precomputed bit masks so the
     // common path is branch-free (boundaries are ~1 in max_nbr columns).
     const int c = warp * 32 + lane;
     const uint32_t bitpos = (uint32_t)((lane & 3) * 8 + (lane >> 2));
     uint32_t icount = 0;
-    if (g.d_pre != nullptr) {
+    if constexpr (kLean) {
       // Lean epilogue: d_pre[e, col] = d_hid * leaky_relu'(pre), one 128-byte line per warp and edge; every
       // segment / rank sum is taken from this copy by the HBM-bound cgat_edge_attn_reduce, so the per-column
       // work here is an add, a select, a multiply and a store.
@@ -147,32 +155,33 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
           const int e0 = e_lo + tile * kBT;
           const int nv = min(kBT, e_hi - e0);
           const uint32_t b = icount & 1u;
+          if ((int)b != grp) continue;
           mbar_wait(&tmem_full[b], (icount >> 1) & 1u);
           tc_fence_after();
           const uint32_t tbase = tmem + ((uint32_t)(warp * 32) << 16) + b * 256;
           float* prow = g.d_pre + (int64_t)e0 * ldd + col;
 #pragma unroll 1
-          for (int cc = 0; cc < kBT / 32; ++cc) {
-            uint32_t wd[32];
-            const uint4* sp = reinterpret_cast<const uint4*>(sg + e0 + cc * 32);
-            const bool aligned = ((reinterpret_cast<uintptr_t>(sp) & 15) == 0) && (cc * 32 + 32 <= nv);
+          for (int cc = 0; cc < kBT / 16; ++cc) {   // 16 columns per batch: 48 live values under the 120-register cap
+            uint32_t wd[16];
+            const uint4* sp = reinterpret_cast<const uint4*>(sg + e0 + cc * 16);
+            const bool aligned = ((reinterpret_cast<uintptr_t>(sp) & 15) == 0) && (cc * 16 + 16 <= nv);
             if (aligned) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) {
+              for (int j = 0; j < 4; ++j) {
                 const uint4 q = kvalid ? __ldg(sp + j) : make_uint4(0, 0, 0, 0);
                 wd[4 * j] = q.x, wd[4 * j + 1] = q.y, wd[4 * j + 2] = q.z, wd[4 * j + 3] = q.w;
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < 32; ++j) wd[j] = (kvalid && cc * 32 + j < nv) ? __ldg(sg + e0 + cc * 32 + j) : 0u;
+              for (int j = 0; j < 16; ++j) wd[j] = (kvalid && cc * 16 + j < nv) ? __ldg(sg + e0 + cc * 16 + j) : 0u;
             }
-            float v[32], w[32];
-            tmem_ld32(tbase + cc * 32, v);
-            tmem_ld32(tbase + 128 + cc * 32, w);
+            float v[16], w[16];
+            tmem_ld16(tbase + cc * 16, v);
+            tmem_ld16(tbase + 128 + cc * 16, w);
             tmem_ld_wait();
-            const int left = kvalid ? nv - cc * 32 : 0;  // columns of this group that are real edges
+            const int left = kvalid ? nv - cc * 16 : 0;  // columns of this group that are real edges
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
+            for (int j = 0; j < 16; ++j) {
               const float dp = fmaf(w[j], corr, v[j]) * (((wd[j] >> bitpos) & 1u) ? s_inv : 0.01f * s_inv);
               if (j < left) *prow = dp;
               prow += ldd;
@@ -182,7 +191,7 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
           mbar_arrive(&tmem_empty[b]);
         }
       }
-    } else
+    } else if (grp == 0)   // kLean == false: the segment-sum form (compiled separately: it needs far more registers)
     for (int item = 0; item < n_items; ++item) {
       const int net = item / (H * nhalf), h = (item / nhalf) % H, half = item % nhalf;
       const int kk = half * 128 + c;
@@ -278,9 +287,9 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
         }
       }
     }
-  } else if (warp < 12) {
+  } else if (warp < kDMmaWarp) {
     // ---------------------------------------------------------------- producers
-    const int pt = tid - 128;
+    const int pt = tid - kDEpilogue;
     uint32_t cnt = 0, icount = 0;
     const uint8_t* wt[2] = {reinterpret_cast<const uint8_t*>(g.wt_a), reinterpret_cast<const uint8_t*>(g.wt_m)};
     const float* dz[2] = {g.d_gate, g.d_msg};
@@ -434,7 +443,7 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_dgrad_kernel(const DgradArg
     }
   }
   __syncthreads();
-  if (warp == 12) {
+  if (warp == kDMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -759,14 +768,15 @@ extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, con
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
-    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     configured = true;
   }
   if (d_pre && row) return fail(-2, "cgat_edge_attn_dgrad: d_pre needs the identity edge order (row == NULL)");
   DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, d_pre, nullptr, ldg,
               col_off, (int)n_atoms, (int)n_edges, heads, hd, n_ranks};
-  edge_dgrad_kernel<false><<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
+  if (d_pre) edge_dgrad_kernel<false, true><<<cgat_edge_attn_dgrad_grid(n_edges), kDThreads, kBSmemBytes, stream>>>(a);
+  else edge_dgrad_kernel<false, false><<<cgat_edge_attn_dgrad_grid(n_edges), kDThreads, kBSmemBytes, stream>>>(a);
   return check_launch("edge_dgrad_kernel");
 }
 
@@ -784,12 +794,12 @@ extern "C" int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg,
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   static bool configured = false;
   if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
+    CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));
     configured = true;
   }
   DgradArgs a{d_gate, d_msg, signs, segptr, seg, nullptr, nullptr, wt_a_packed, wt_m_packed, nullptr, nullptr, d_pre,
               dz_amax, 0, 0, (int)n_atoms, (int)n_edges, heads, hd, 1};
-  edge_dgrad_kernel<true><<<cgat_edge_attn_dgrad_grid(n_edges), kBThreads, kBSmemBytes, stream>>>(a);
+  edge_dgrad_kernel<true, true><<<cgat_edge_attn_dgrad_grid(n_edges), kDThreads, kBSmemBytes, stream>>>(a);
   return check_launch("edge_dgrad_f16_kernel");
 }
 
