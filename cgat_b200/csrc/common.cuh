@@ -55,14 +55,17 @@ inline int hyper_chunk(int64_t n_atoms, int f) {
 // (this CTA) - (first CTA that touches the tile).  hyper_slots() bounds that slot count: with >= per = floor(items /
 // grid) items per CTA a tile's n_chunks items meet at most ceil(n_chunks / per) + 1 CTAs.  (Round 1 wrote one partial
 // per chunk: 16 x N x F floats per launch at the bench size instead of 5, all re-read by the partial sum.)
-inline int hyper_grid(int64_t n_atoms, int f) {
-  const int64_t n_items = ((n_atoms + 127) / 128) * (f / hyper_chunk(n_atoms, f));
+inline int64_t hyper_items(int64_t n_atoms, int f, int mode) {
+  // forward (mode 0): (atom tile, output chunk); backward (mode 1): ((atom tile, 128-column half), output chunk)
+  return ((n_atoms + 127) / 128) * (mode ? f / 128 : 1) * (f / hyper_chunk(n_atoms, f));
+}
+inline int hyper_grid(int64_t n_atoms, int f, int mode = 0) {
+  const int64_t n_items = hyper_items(n_atoms, f, mode);
   return (int)(n_items < kNumSMs ? (n_items > 0 ? n_items : 1) : kNumSMs);
 }
 inline int hyper_slots(int64_t n_atoms, int f) {
   const int n_chunks = f / hyper_chunk(n_atoms, f);
-  const int64_t n_items = ((n_atoms + 127) / 128) * n_chunks;
-  const int64_t per = n_items / hyper_grid(n_atoms, f);
+  const int64_t per = hyper_items(n_atoms, f, 1) / hyper_grid(n_atoms, f, 1);
   const int64_t s = per > 0 ? (n_chunks + per - 1) / per + 1 : n_chunks;
   return (int)(s < n_chunks ? s : n_chunks);
 }

@@ -43,11 +43,11 @@ constexpr int kEMmaWarp = (kEEpilogue + kEProducers) / 32;
 constexpr int kEThreads = kEEpilogue + kEProducers + 32;
 constexpr int kEStages = 3;
 constexpr int kEStageBytes = 2 * (int)kPackStageBytes;  // [W2 chunk hi|lo][hidden chunk hi|lo]
-constexpr int kEMaxHeads = 8;
+constexpr int kEMaxHeads = 16;         // VIRTUAL heads: (real head, 128-channel block of its F output channels)
 constexpr int kEMetaBufs = 4;          // tile metadata ring (producers run ahead of the epilogue)
 constexpr int kEMetaStride = 4 * kET + 8;  // dst | src | rank | dst*H*F | 4 words segment-start flags | 4 words valid mask
 constexpr int kEMetaBytes = kEMetaBufs * kEMetaStride * 4;
-constexpr int kECarryBytes = kEMaxHeads * 4 * kEF * 4;  // (max, den, acc, open dst) per head and channel
+constexpr int kECarryBytes = kEMaxHeads * 3 * kEF * 4 + kEMaxHeads * 4;  // (max, den, acc) per head and channel + open dst per head
 constexpr int kESmemBytes = kEStages * kEStageBytes + kEMetaBytes + kECarryBytes + 256 + 1024;
 
 struct EdgeArgs {
@@ -70,9 +70,10 @@ struct EdgeArgs {
   uint32_t* signs;      // backward-prep: [2][H][kcn][E] LeakyReLU side of the 32 hidden units of a chunk
   float* bias_sums;     // backward-prep (optional): (grid, 2, H, F) per-CTA column sums of d_msg | d_gate = dL/d b2
   unsigned int* dz_amax;  // backward-prep (optional): max |d_gate|, |d_msg| as float bits (range of the f16 wgrad / dgrad)
-  int n_atoms, n_edges, heads, hd;
+  int n_atoms, n_edges, heads, hd;   // heads = VIRTUAL heads = real heads * vh
   float eps;
   int n_stages;         // operand ring depth: 3, or 2 with L1 prefetch of the gathered rows (f16 path)
+  int vh;               // 128-channel blocks per real head (F / 128): F = 256 runs every real head as two virtual heads
 };
 
 __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int64_t key) {
@@ -140,7 +141,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
   int32_t* range = reinterpret_cast<int32_t*>(tmem_slot + 1);  // e_lo, e_hi
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int H = g.heads, hd = g.hd, hhd = H * hd;
+  // H counts VIRTUAL heads: output channels [h*128, h*128+128) of the (N, H_real, F) tensors, rows h*128.. of the
+  // packed W2; virtual head h reads the hidden units of real head h / vh
+  const int H = g.heads, hd = g.hd, vh = g.vh, HR = H / vh, hhd = HR * hd;
   constexpr int kChunk = kF16 ? kPackChunk16 : kPackChunk;  // hidden units per pipeline stage
   const int kcn = (hd + kChunk - 1) / kChunk;
   const float acc_scale = kF16 ? kF16AccInv : 1.f;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
   if (kMode == 1 && tid < kEEpilogue) {
     // backward-prep does not carry softmax state across tiles; the buffer holds the per-CTA column sums of
     // d_msg / d_gate instead (the bias gradients of the second layer): [epilogue group][d_msg | d_gate][head][channel]
-    for (int i = tid; i < kECarryBytes / 4; i += kEEpilogue) carry[i] = 0.f;
+    for (int i = tid; i < 2 * 2 * 8 * kEF; i += kEEpilogue) carry[i] = 0.f;   // 16 KB: [2][2][8] or [2][16] x 128
   }
   tc_fence_before();
   __syncthreads();
@@ -198,7 +201,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
       for (int h = 0; h < H; ++h, ++hcount) {
         const uint32_t hb = hcount & 1u;
         if ((int)hb != grp) continue;
-        float* cs = carry + (h * 4) * kEF;
+        float* cs = carry + (h * 3) * kEF;
+        int* cd = reinterpret_cast<int*>(carry + kEMaxHeads * 3 * kEF) + h;   // the open destination of head h
         const int hc = h * kEF + c;
         const float ba = __ldg(g.b2a + hc), bm = __ldg(g.b2m + hc);
         mbar_wait(&tmem_full[hb], (hcount >> 1) & 1u);
@@ -209,7 +213,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           int d = -1;
           if (tile > 0) {
             mbar_wait(&carry_bar[h], (uint32_t)(tile - 1) & 1u);  // written by the group that had (tile-1, h)
-            m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = __float_as_int(cs[3 * kEF + c]);
+            m = cs[c], den = cs[kEF + c], acc = cs[2 * kEF + c], d = *cd;
           }
           {  // tile start: the one place that needs a compare against the carried segment
             const int d0 = mt[0];
@@ -258,7 +262,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             g.out[o] = acc / (den + g.eps);
             if (g.smax) g.smax[o] = m, g.sden[o] = den;
           } else {
-            cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc, cs[3 * kEF + c] = __int_as_float(d);
+            cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc;
+            if (c == 0) *cd = d;
             mbar_arrive(&carry_bar[h]);
           }
         } else {
@@ -297,9 +302,11 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           }
           tc_fence_before();
           mbar_arrive(&tmem_empty[hb]);
-          // only this thread ever touches these two words: group grp handles its items one after the other
-          carry[((grp * 2 + 0) * kEMaxHeads + h) * kEF + c] += sum_m;
-          carry[((grp * 2 + 1) * kEMaxHeads + h) * kEF + c] += sum_g;
+          // only this thread ever touches these two words: group grp handles its items one after the other.  With an
+          // even head count a head always meets the same group (item parity = head parity): one array; else one per group
+          const int gi = (H & 1) ? grp : 0, hs = (H & 1) ? 8 : 16;
+          carry[((gi * 2 + 0) * hs + h) * kEF + c] += sum_m;
+          carry[((gi * 2 + 1) * hs + h) * kEF + c] += sum_g;
         }
       }
     }
@@ -356,7 +363,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               // slot = (edge row r, 16-byte chunk c) = 8 consecutive hidden units: two float4 from each of the three
               // gathered rows; two slots at a time (12 float4 in flight, like the tf32 path)
               uint8_t* bh = st + kPackStageBytes;
-              const int col0 = h * hd + kc * kPackChunk16;
+              const int col0 = (h / vh) * hd + kc * kPackChunk16;
 #pragma unroll 1
               for (int j0 = 0; j0 < 4; j0 += 2) {
                 float4 pd[2][2], ps[2][2], te[2][2];
@@ -400,8 +407,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                     part |= __shfl_xor_sync(0xffffffffu, part, 1);
                     part |= __shfl_xor_sync(0xffffffffu, part, 2);
                     const int r = idx >> 3;
-                    if ((lane & 3) == 0 && r < nv)
-                      g.signs[((int64_t)(net * H + h) * (2 * kcn) + 2 * kc + (c >> 2)) * g.n_edges + e0 + r] = part;
+                    if ((lane & 3) == 0 && r < nv && h % vh == 0)   // one sign word per REAL head
+                      g.signs[((int64_t)(net * HR + h / vh) * (2 * kcn) + 2 * kc + (c >> 2)) * g.n_edges + e0 + r] = part;
                   }
 #pragma unroll
                   for (int t = 0; t < 8; ++t) x[t] = lrelu(x[t]) * kHidScale;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               }
             } else {
               float4 pd[4], ps[4], te[4];
-              const int col0 = h * hd + kc * 32;
+              const int col0 = (h / vh) * hd + kc * 32;
   #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const int cch = (pl + kEGroup * j) & 7;
@@ -445,8 +452,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                   const uint32_t word = ((b0 >> sh) & 0xFFu) | (((b1 >> sh) & 0xFFu) << 8) | (((b2 >> sh) & 0xFFu) << 16) |
                                         (((b3 >> sh) & 0xFFu) << 24);
                   const int r = idx >> 3;
-                  if ((lane & 7) == 0 && r < nv)
-                    g.signs[((int64_t)(net * H + h) * kcn + kc) * g.n_edges + e0 + r] = word;
+                  if ((lane & 7) == 0 && r < nv && h % vh == 0)
+                    g.signs[((int64_t)(net * HR + h / vh) * kcn + kc) * g.n_edges + e0 + r] = word;
                 }
                 x.x = lrelu(x.x), x.y = lrelu(x.y), x.z = lrelu(x.z), x.w = lrelu(x.w);
                 float4 hi, lo;
@@ -471,7 +478,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
                   if (++net2 == 2) net2 = 0, ++h2;
                 }
               if (h2 < H && (pl & 3) == 0) {  // one thread per 128-byte line: chunks 0-3 / 4-7 of a 256-byte row slice
-                const int colp = net2 * hhd + h2 * hd + kc2 * kPackChunk16 + ((pl >> 2) & 1) * 32;
+                const int colp = net2 * hhd + (h2 / vh) * hd + kc2 * kPackChunk16 + ((pl >> 2) & 1) * 32;
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                   const int r = (pl + kEGroup * j) >> 3;
@@ -533,7 +540,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     float* dst = g.bias_sums + (int64_t)blockIdx.x * 2 * H * kEF;
     for (int i = tid; i < 2 * H * kEF; i += kEThreads) {
       const int which = i / (H * kEF), hc = i - which * H * kEF, h = hc / kEF, c = hc - h * kEF;
-      dst[i] = carry[((0 * 2 + which) * kEMaxHeads + h) * kEF + c] + carry[((1 * 2 + which) * kEMaxHeads + h) * kEF + c];
+      dst[i] = (H & 1) ? carry[((0 * 2 + which) * 8 + h) * kEF + c] + carry[((1 * 2 + which) * 8 + h) * kEF + c]
+                       : carry[(which * 16 + h) * kEF + c];
     }
   }
   if (warp == kEMmaWarp) {
@@ -549,8 +557,8 @@ using namespace cgat;
 
 namespace {
 int check_edge_args(int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, int32_t hd) {
-  if (f != kEF) return fail(-2, "cgat_edge_attn_*: only F = 128 (vector attention) is instantiated");
-  if (heads < 1 || heads > kEMaxHeads) return fail(-2, "cgat_edge_attn_*: heads must be in [1,8]");
+  if (f != kEF && f != 2 * kEF) return fail(-2, "cgat_edge_attn_*: F must be 128 or 256 (vector attention)");
+  if (heads < 1 || heads * (f / kEF) > kEMaxHeads) return fail(-2, "cgat_edge_attn_*: heads * F / 128 must be in [1,16]");
   if (hd <= 0 || (hd & 3)) return fail(-2, "cgat_edge_attn_*: hidden width must be a multiple of 4");
   if (n_atoms * heads * f >= (1ll << 31) || n_edges >= (1ll << 31) - 129) return fail(-2, "cgat_edge_attn_*: size overflow");
   return 0;
@@ -605,7 +613,8 @@ int edge_fwd_impl(const float* P, const float* T, const int32_t* rowptr, const i
   }
   if (n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
-             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads, hd, eps};
+             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads * (f / kEF), hd,
+             eps, 0, f / kEF};
   return launch_edge<0, kF16>(a, stream);
 }
 
@@ -623,7 +632,8 @@ int edge_bwd_prep_impl(const float* P, const float* T, const int32_t* rowptr, co
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
              const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs, bias_sums,
-             reinterpret_cast<unsigned int*>(dz_amax), (int)n_atoms, (int)n_edges, heads, hd, eps};
+             reinterpret_cast<unsigned int*>(dz_amax), (int)n_atoms, (int)n_edges, heads * (f / kEF), hd, eps, 0,
+             f / kEF};
   return launch_edge<1, kF16>(a, stream);
 }
 }  // namespace

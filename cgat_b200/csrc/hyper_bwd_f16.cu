@@ -170,17 +170,164 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
   }
 }
 
+// ---- F = 256 (BASELINE.json configs[3]) --------------------------------------------------------------------------
+// One CTA = (output channel o, 128-row half of its F x F block, atom range): A = g[:,o] * y[:, half] (128 columns),
+// B = z (256 columns) -> one N = 256 accumulator (main | correction = all 512 TMEM columns).  Same stage size (48 KB).
+constexpr int kF2 = 256;
+constexpr int kPartZ2 = 4 * kImg;              // 256 columns = 4 images = 16 KB
+constexpr int kStage2 = 2 * kPartZ2 + 2 * kPart;   // Z hi/lo + A hi/lo = 48 KB
+
+__global__ void __launch_bounds__(kThreadsW, 1)
+hyper_wgrad_f16_256_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ z,
+                           const float* __restrict__ g_amax, float* __restrict__ out, int n_atoms, int n_split) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * kStage2);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStagesW;
+  uint64_t* accum = bars + 2 * kStagesW;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int item = blockIdx.x / n_split, split = blockIdx.x % n_split;
+  const int o = item >> 1, half = item & 1;
+  const int n_lo = (int)((int64_t)n_atoms * split / n_split), n_hi = (int)((int64_t)n_atoms * (split + 1) / n_split);
+  const int n_chunks = (n_hi - n_lo + kRows - 1) / kRows;
+  const float amax = __ldg(g_amax);
+  int ex;
+  frexpf(amax, &ex);
+  const float s = (amax > 0.f && amax < INFINITY) ? ldexpf(1.f, 4 - ex) : 1.f;
+  const float s_inv = (amax > 0.f && amax < INFINITY) ? ldexpf(1.f, ex - 4) : 1.f;
+
+  if (tid == 0) {
+    for (int st = 0; st < kStagesW; ++st) {
+      mbar_init(&full[st], 256);
+      mbar_init(&empty[st], 1);
+    }
+    mbar_init(accum, 1);
+    mbar_init_fence();
+  }
+  if (warp == kMmaWarpW) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp < 4) {
+    const int i = warp * 32 + lane;  // row of the half block = input channel half*128 + i
+    mbar_wait(accum, 0);
+    tc_fence_after();
+    float* dst = out + ((int64_t)split * kF2 * kF2 + (int64_t)o * kF2 + half * 128 + i) * kF2;
+#pragma unroll 1
+    for (int cc = 0; cc < 8; ++cc) {
+      float v[32], w[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 256 + cc * 32, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 r;
+        r.x = n_chunks ? fmaf(w[4 * j], kF16LoInv, v[4 * j]) * s_inv : 0.f;
+        r.y = n_chunks ? fmaf(w[4 * j + 1], kF16LoInv, v[4 * j + 1]) * s_inv : 0.f;
+        r.z = n_chunks ? fmaf(w[4 * j + 2], kF16LoInv, v[4 * j + 2]) * s_inv : 0.f;
+        r.w = n_chunks ? fmaf(w[4 * j + 3], kF16LoInv, v[4 * j + 3]) * s_inv : 0.f;
+        reinterpret_cast<float4*>(dst + cc * 32)[j] = r;
+      }
+    }
+    tc_fence_before();
+  } else if (warp < kMmaWarpW) {
+    const int pt = tid - 128, grp = pt >> 8, pl = pt & 255;
+    for (int ch = grp; ch < n_chunks; ch += 2) {
+      const int st = ch % kStagesW, u = ch / kStagesW;
+      const int n0 = n_lo + ch * kRows;
+      float4 zv[8], yv[4];
+      float gs[4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {   // z: 32 rows x 64 float4
+        const int idx = pl + 256 * j, r = idx >> 6, q = idx & 63;
+        const int n = n0 + r;
+        zv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (n < n_hi) zv[j] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)n * kF2) + q);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {   // y half: 32 rows x 32 float4
+        const int idx = pl + 256 * j, r = idx >> 5, q = idx & 31;
+        const int n = n0 + r;
+        yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        gs[j] = 0.f;
+        if (n < n_hi) {
+          yv[j] = __ldg(reinterpret_cast<const float4*>(y + (int64_t)n * kF2 + half * 128) + q);
+          gs[j] = __ldg(g + (int64_t)n * kF2 + o) * s;
+        }
+      }
+      mbar_wait(&empty[st], (u + 1) & 1u);
+      uint8_t* sb = smem + st * kStage2;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int idx = pl + 256 * j, r = idx >> 6, q = idx & 63;
+        const uint32_t off = (q >> 4) * kImg + mn16_offset(r, q & 15);
+        uint2 hi, lo;
+        split_f16x4s(zv[j], kF16LoScale, hi, lo);
+        *reinterpret_cast<uint2*>(sb + off) = hi;
+        *reinterpret_cast<uint2*>(sb + kPartZ2 + off) = lo;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int idx = pl + 256 * j, r = idx >> 5, q = idx & 31;
+        const uint32_t off = (q >> 4) * kImg + mn16_offset(r, q & 15);
+        const float4 a = make_float4(yv[j].x * gs[j], yv[j].y * gs[j], yv[j].z * gs[j], yv[j].w * gs[j]);
+        uint2 hi, lo;
+        split_f16x4s(a, kF16LoScale, hi, lo);
+        *reinterpret_cast<uint2*>(sb + 2 * kPartZ2 + off) = hi;
+        *reinterpret_cast<uint2*>(sb + 2 * kPartZ2 + kPart + off) = lo;
+      }
+      fence_async_smem();
+      mbar_arrive(&full[st]);
+    }
+  } else {
+    constexpr uint32_t idesc = umma_idesc_f16_mn(128, 256);
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      const int st = ch % kStagesW, u = ch / kStagesW;
+      mbar_wait(&full[st], u & 1u);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t z_hi = smem_u32(smem + st * kStage2), z_lo = z_hi + kPartZ2;
+        const uint32_t a_hi = z_hi + 2 * kPartZ2, a_lo = a_hi + kPart;
+#pragma unroll
+        for (int ks = 0; ks < kRows / 16; ++ks) {
+          const uint32_t o2 = ks * 2048;
+          umma_f16(tmem + 256, umma_desc_mn_sw128_16b(a_lo + o2, kImg), umma_desc_mn_sw128_16b(z_hi + o2, kImg), idesc,
+                   (ch | ks) != 0);
+          umma_f16(tmem + 256, umma_desc_mn_sw128_16b(a_hi + o2, kImg), umma_desc_mn_sw128_16b(z_lo + o2, kImg), idesc, 1);
+          umma_f16(tmem, umma_desc_mn_sw128_16b(a_hi + o2, kImg), umma_desc_mn_sw128_16b(z_hi + o2, kImg), idesc,
+                   (ch | ks) != 0);
+        }
+        umma_commit(&empty[st]);
+        if (ch == n_chunks - 1) umma_commit(accum);
+      }
+      __syncwarp();
+    }
+    if (n_chunks == 0 && lane == 0) mbar_arrive(accum);
+  }
+  __syncthreads();
+  if (warp == kMmaWarpW) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 }  // namespace
 }  // namespace cgat
 
 using namespace cgat;
 
-// cgat_hyper_wgrad on kind::f16 passes: same result layout, (cgat_hyper_wgrad_splits(N), F*F, F) partial dL/dW[:F*F].
+// cgat_hyper_wgrad on kind::f16 passes: same result layout, (cgat_hyper_wgrad_splits(N), F*F, F) partial dL/dW[:F*F]
+// for F = 128; for F = 256 a single (F*F, F) result (no split over atoms).
 // g_amax: device float holding max |g| (written by cgat_hyper_rowscale_f16 with the same g as `scale`).
 extern "C" int cgat_hyper_wgrad_f16(const float* g, const float* y, const float* z, const float* g_amax, float* out,
                                     int64_t n_atoms, int32_t f, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (f != kF) return fail(-2, "cgat_hyper_wgrad_f16: only F = 128 is instantiated");
+  if (f != kF && f != kF2) return fail(-2, "cgat_hyper_wgrad_f16: instantiated for F = 128 and F = 256");
   if (n_atoms >= (1ll << 31) - 64) return fail(-2, "cgat_hyper_wgrad_f16: too many atoms");
   if (g_amax == nullptr) return fail(-2, "cgat_hyper_wgrad_f16: g_amax is required");
   if (n_atoms <= 0) return 0;
@@ -188,6 +335,16 @@ extern "C" int cgat_hyper_wgrad_f16(const float* g, const float* y, const float*
   if (!configured) {
     CGAT_CUDA(cudaFuncSetAttribute(hyper_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW));
     configured = true;
+  }
+  if (f == kF2) {
+    // (o, row half) x splits: 512 CTAs already fill the SMs three times over, so the atoms are not split
+    static bool configured2 = false;
+    if (!configured2) {
+      CGAT_CUDA(cudaFuncSetAttribute(hyper_wgrad_f16_256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW));
+      configured2 = true;
+    }
+    hyper_wgrad_f16_256_kernel<<<2 * f, kThreadsW, kSmemW, stream>>>(g, y, z, g_amax, out, (int)n_atoms, 1);
+    return check_launch("hyper_wgrad_f16_256_kernel");
   }
   const int n_split = cgat_hyper_wgrad_splits(n_atoms);
   hyper_wgrad_f16_kernel<<<(f / 2) * n_split, kThreadsW, kSmemW, stream>>>(g, y, z, g_amax, out, (int)n_atoms, n_split);

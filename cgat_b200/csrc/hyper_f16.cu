@@ -22,21 +22,26 @@ using namespace tc;
 
 template <int F>
 struct Hyper16Cfg {
+  static constexpr int kNH = F / 128;                           // 128-column halves of a predicted-weight row (F = 256: 2)
   static constexpr int kKC = F / kPackChunk16;                  // K chunks of 64 halves (one 128-byte swizzled row)
-  static constexpr int kABytes = kKC * (int)kPackStageBytes;    // activation tile, hi+lo per chunk: 64 KB
-  static constexpr int kStages = 4;                             // 32 KB weight stages
+  static constexpr int kABytes = kKC * (int)kPackStageBytes;    // activation tile, hi+lo per chunk: 64 KB (F = 256: 128 KB)
+  static constexpr int kStages = F == 128 ? 4 : 2;              // 32 KB weight stages
   static constexpr int kRedBytes = 4 * 16 * 128 * 4;            // forward: [column group][output of the item][atom row]
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + kRedBytes + 1024 + kBarBytes;
   static constexpr int kEpiWarps = 16;                          // 4 column groups x 4 lane quadrants
   static constexpr int kEpiThreads = kEpiWarps * 32;
   static constexpr int kThreads = kEpiThreads + 128 + 32;       // + stagers + MMA warp
-  static constexpr int kTmemCols = 4 * F;                       // two buffers x (main, correction)
+  static constexpr int kTmemCols = 512;                         // two buffers x (main, correction) x 128 columns
 };
 
 // kMode 0 (forward):   y_out[n,o] = sum_j D_o[n,j] * y_in[n,j] + e_term[n,o]
 // kMode 1 (backward):  partial[chunk][n,j] = sum_{o in chunk} y_in[n,o] * D_o[n,j]
 //   D_o[n,j] = sum_m z[n,m] Wblk_o[j,m] (+ w_bias[o*F+j]);  see hyper_fwd.cu for the two backward uses.
+// F = 256 (BASELINE.json configs[3], the wider net): a predicted-weight row D_o[n, :] has two 128-column halves, each
+// its own 128-row tile of the packed weight and its own accumulator pass.  Forward walks both halves inside a work
+// item (the half dot products meet in `red`); backward makes (atom tile, half) a "virtual tile" of the item index, so
+// that a CTA's register accumulators still cover exactly one 128-column block of the result.
 template <int F, int kMode>
 __global__ void __launch_bounds__(Hyper16Cfg<F>::kThreads, 1)
 hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
@@ -44,7 +49,9 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
                         const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc, int n_slots,
                         unsigned int* __restrict__ scale_amax) {
   using Cfg = Hyper16Cfg<F>;
-  static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
+  static_assert(F == 128 || F == 256, "instantiated for F = 128 and F = 256");
+  constexpr int NH = Cfg::kNH;
+  constexpr int kHalvesPerItem = kMode == 0 ? NH : 1;   // forward: both halves inside the item; backward: half = part of the tile
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                   // [kKC][hi|lo][16 KB]
@@ -62,8 +69,9 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n_tiles = (n_atoms + 127) / 128;
   const int n_chunks = F / oc;
-  const int n_items = n_tiles * n_chunks;
-  // work item = (atom tile, chunk of output channels), chunk fastest; contiguous item range per CTA
+  const int n_vt = kMode == 0 ? n_tiles : n_tiles * NH;   // (virtual) tiles: backward splits a tile into its column halves
+  const int n_items = n_vt * n_chunks;
+  // work item = ((virtual) atom tile, chunk of output channels), chunk fastest; contiguous item range per CTA
   const int item_lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x);
   const int item_hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
 
@@ -93,7 +101,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     // of every accumulator, so a thread keeps a quarter of its atom's row.  kMode 0: the four partial dot products of
     // an output meet in shared memory (red[grp][output][row], conflict-free) and are summed, together with the e
     // term, by all 512 threads once per work item; kMode 1 needs no exchange.
-    constexpr int QF = F / 4;
+    constexpr int QF = 32;   // a thread keeps a quarter of a 128-column half of its atom's row
     const int grp = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
@@ -101,68 +109,76 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     float y[QF];
     float sc_max = 0.f;   // kMode 1: max |scale| seen by this thread (the gradient operand of the weight-gradient kernel)
     for (int item = item_lo; item < item_hi; ++item) {
-      const int tile = item / n_chunks, chunk = item - tile * n_chunks;
+      const int vt = item / n_chunks, chunk = item - vt * n_chunks;
+      const int tile = kMode == 0 ? vt : vt / NH, vhalf = kMode == 0 ? 0 : vt % NH;
       const int n = tile * 128 + row;
       const bool valid = n < n_atoms;
-      // kMode 0: this atom's quarter y_in row; kMode 1: the running partial sums over o, carried across the
-      // consecutive chunks of one tile (a new run starts with the CTA's first item or a tile's first chunk)
-      if (kMode == 0 || item == item_lo || chunk == 0) {
+      for (int hh = 0; hh < kHalvesPerItem; ++hh) {
+        const int half = kMode == 0 ? hh : vhalf;
+        // kMode 0: this atom's quarter of the y_in half; kMode 1: the running partial sums over o, carried across the
+        // consecutive chunks of one virtual tile (a new run starts with the CTA's first item or a tile's first chunk)
+        if (kMode == 0 || item == item_lo || chunk == 0) {
 #pragma unroll
-        for (int j = 0; j < QF / 4; ++j) {
-          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kMode == 0 && valid) t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + grp * QF) + j);
-          y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+          for (int j = 0; j < QF / 4; ++j) {
+            float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (kMode == 0 && valid)
+              t = __ldg(reinterpret_cast<const float4*>(y_in + (int64_t)n * F + half * 128 + grp * QF) + j);
+            y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
+          }
         }
-      }
-      for (int oi = 0; oi < oc; ++oi, ++ocount) {
-        const int o = chunk * oc + oi;
-        const uint32_t b = ocount & 1u;
-        const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
-        if (kMode == 1) sc_max = fmaxf(sc_max, fabsf(sc));
-        // The bias of the predicted weight row, p[n, o*F + j] = D_o[n, j] + bl[o*F + j], does not depend on the MMAs:
-        // its contribution is taken BEFORE waiting for the accumulator (broadcast loads: every thread of a column
-        // group reads the same 32 floats), so only tcgen05.ld + two FMAs per element sit behind the barrier.
-        float acc = 0.f;
-        if (w_bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(w_bias + (int64_t)o * F + grp * QF);
+        for (int oi = 0; oi < oc; ++oi, ++ocount) {
+          const int o = chunk * oc + oi;
+          const uint32_t b = ocount & 1u;
+          const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
+          if (kMode == 1) sc_max = fmaxf(sc_max, fabsf(sc));
+          // The bias of the predicted weight row, p[n, o*F + j] = D_o[n, j] + bl[o*F + j], does not depend on the MMAs:
+          // its contribution is taken BEFORE waiting for the accumulator (broadcast loads: every thread of a column
+          // group reads the same 32 floats), so only tcgen05.ld + two FMAs per element sit behind the barrier.
+          float acc = 0.f;
+          if (w_bias != nullptr) {
+            const float4* bp = reinterpret_cast<const float4*>(w_bias + (int64_t)o * F + half * 128 + grp * QF);
 #pragma unroll
-          for (int q = 0; q < QF / 4; ++q) {
-            const float4 b4 = __ldg(bp + q);
-            if (kMode == 0) {
-              acc = fmaf(b4.x, y[4 * q], acc), acc = fmaf(b4.y, y[4 * q + 1], acc);
-              acc = fmaf(b4.z, y[4 * q + 2], acc), acc = fmaf(b4.w, y[4 * q + 3], acc);
-            } else {
-              y[4 * q] = fmaf(b4.x, sc, y[4 * q]), y[4 * q + 1] = fmaf(b4.y, sc, y[4 * q + 1]);
-              y[4 * q + 2] = fmaf(b4.z, sc, y[4 * q + 2]), y[4 * q + 3] = fmaf(b4.w, sc, y[4 * q + 3]);
+            for (int q = 0; q < QF / 4; ++q) {
+              const float4 b4 = __ldg(bp + q);
+              if (kMode == 0) {
+                acc = fmaf(b4.x, y[4 * q], acc), acc = fmaf(b4.y, y[4 * q + 1], acc);
+                acc = fmaf(b4.z, y[4 * q + 2], acc), acc = fmaf(b4.w, y[4 * q + 3], acc);
+              } else {
+                y[4 * q] = fmaf(b4.x, sc, y[4 * q]), y[4 * q + 1] = fmaf(b4.y, sc, y[4 * q + 1]);
+                y[4 * q + 2] = fmaf(b4.z, sc, y[4 * q + 2]), y[4 * q + 3] = fmaf(b4.w, sc, y[4 * q + 3]);
+              }
             }
           }
-        }
-        mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
-        tc_fence_after();
-        const uint32_t tb = tmem + lane_base + b * 2 * F + grp * QF;
-        // 8 columns per batch (80 registers per thread with 21 warps, 32 of them hold the row values), software
-        // pipelined: the loads of batch cc+1 are in flight while batch cc is consumed.  v = hi*hi products,
-        // w = (hi*lo + lo*hi products) * 2^11.
-        float v[2][8], w[2][8];
-        tmem_ld8(tb, v[0]);
-        tmem_ld8(tb + F, w[0]);
+          mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
+          tc_fence_after();
+          const uint32_t tb = tmem + lane_base + b * 256 + grp * QF;
+          // 8 columns per batch (80 registers per thread with 21 warps, 32 of them hold the row values), software
+          // pipelined: the loads of batch cc+1 are in flight while batch cc is consumed.  v = hi*hi products,
+          // w = (hi*lo + lo*hi products) * 2^11.
+          float v[2][8], w[2][8];
+          tmem_ld8(tb, v[0]);
+          tmem_ld8(tb + 128, w[0]);
 #pragma unroll
-        for (int cc = 0; cc < QF / 8; ++cc) {
-          tmem_ld_wait();
-          if (cc + 1 < QF / 8) {
-            tmem_ld8(tb + (cc + 1) * 8, v[(cc + 1) & 1]);
-            tmem_ld8(tb + F + (cc + 1) * 8, w[(cc + 1) & 1]);
-          }
+          for (int cc = 0; cc < QF / 8; ++cc) {
+            tmem_ld_wait();
+            if (cc + 1 < QF / 8) {
+              tmem_ld8(tb + (cc + 1) * 8, v[(cc + 1) & 1]);
+              tmem_ld8(tb + 128 + (cc + 1) * 8, w[(cc + 1) & 1]);
+            }
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float t = fmaf(w[cc & 1][j], kF16LoInv, v[cc & 1][j]);
-            if (kMode == 0) acc = fmaf(t, y[cc * 8 + j], acc);
-            else y[cc * 8 + j] = fmaf(t, sc, y[cc * 8 + j]);
+            for (int j = 0; j < 8; ++j) {
+              const float t = fmaf(w[cc & 1][j], kF16LoInv, v[cc & 1][j]);
+              if (kMode == 0) acc = fmaf(t, y[cc * 8 + j], acc);
+              else y[cc * 8 + j] = fmaf(t, sc, y[cc * 8 + j]);
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&tmem_empty[b]);
+          if (kMode == 0) {
+            float* rp = red + (grp * 16 + oi) * 128 + row;   // only this thread touches the word: halves add up in place
+            *rp = hh == 0 ? acc : *rp + acc;
           }
         }
-        tc_fence_before();
-        mbar_arrive(&tmem_empty[b]);
-        if (kMode == 0) red[(grp * 16 + oi) * 128 + row] = acc;
       }
       if (kMode == 0) {
         asm volatile("bar.sync 2, %0;" ::"n"(Cfg::kEpiThreads) : "memory");  // all partials of this item are in `red`
@@ -185,15 +201,16 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
         asm volatile("bar.sync 3, %0;" ::"n"(Cfg::kEpiThreads) : "memory");  // `red` may be overwritten by the next item
       }
       if (kMode == 1 && valid && (item + 1 == item_hi || chunk == n_chunks - 1)) {
-        // end of this CTA's run on the tile: one partial per (CTA, tile); the CTA that finishes the tile also clears
-        // the slots nobody used (the caller sums all n_slots)
-        const int slot = (int)blockIdx.x - hyper_cta_of_item((int64_t)tile * n_chunks, n_items, (int)gridDim.x);
-        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)slot * n_atoms + n) * F + grp * QF);
+        // end of this CTA's run on the (virtual) tile: one partial per (CTA, tile); the CTA that finishes the tile also
+        // clears the slots nobody used (the caller sums all n_slots)
+        const int slot = (int)blockIdx.x - hyper_cta_of_item((int64_t)vt * n_chunks, n_items, (int)gridDim.x);
+        const int64_t col = vhalf * 128 + grp * QF;
+        float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)slot * n_atoms + n) * F + col);
 #pragma unroll
         for (int j = 0; j < QF / 4; ++j) dst[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
         if (chunk == n_chunks - 1)
           for (int sl = slot + 1; sl < n_slots; ++sl) {
-            float4* z4 = reinterpret_cast<float4*>(y_out + ((int64_t)sl * n_atoms + n) * F + grp * QF);
+            float4* z4 = reinterpret_cast<float4*>(y_out + ((int64_t)sl * n_atoms + n) * F + col);
 #pragma unroll
             for (int j = 0; j < QF / 4; ++j) z4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
           }
@@ -214,7 +231,8 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     uint32_t it = 0, cnt = 0;
     int staged_tile = -1;
     for (int item = item_lo; item < item_hi; ++item) {
-      const int tile = item / n_chunks, chunk = item - tile * n_chunks;
+      const int vt = item / n_chunks, chunk = item - vt * n_chunks;
+      const int tile = kMode == 0 ? vt : vt / NH, vhalf = kMode == 0 ? 0 : vt % NH;
       const bool restage = tile != staged_tile;
       staged_tile = tile;
       if (restage) mbar_wait(a_free, (it + 1) & 1u);  // the previous tile's MMAs have finished reading the tile
@@ -254,14 +272,17 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
       }
       if (st == 0) {
         const uint8_t* wsrc = reinterpret_cast<const uint8_t*>(w_packed);
-        for (int oi = 0; oi < oc; ++oi) {
-          const int o = chunk * oc + oi;
-          for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
-            const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
-            mbar_wait(&empty[s], (u + 1) & 1u);
-            mbar_arrive_expect_tx(&full[s], kPackStageBytes);
-            bulk_g2s(b_smem + s * kPackStageBytes, wsrc + ((int64_t)o * Cfg::kKC + kc) * kPackStageBytes,
-                     kPackStageBytes, &full[s]);
+        for (int hh = 0; hh < kHalvesPerItem; ++hh) {
+          const int half = kMode == 0 ? hh : vhalf;
+          for (int oi = 0; oi < oc; ++oi) {
+            const int64_t rt = (int64_t)(chunk * oc + oi) * NH + half;   // 128-row tile of the packed weight
+            for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
+              const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
+              mbar_wait(&empty[s], (u + 1) & 1u);
+              mbar_arrive_expect_tx(&full[s], kPackStageBytes);
+              bulk_g2s(b_smem + s * kPackStageBytes, wsrc + (rt * Cfg::kKC + kc) * kPackStageBytes, kPackStageBytes,
+                       &full[s]);
+            }
           }
         }
       }
@@ -269,18 +290,19 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(128, F), idesc2 = umma_idesc_f16(128, 2 * F);
+    constexpr uint32_t idesc = umma_idesc_f16(128, 128), idesc2 = umma_idesc_f16(128, 256);
     uint32_t it = 0, cnt = 0, ocount = 0;
     int staged_tile = -1;
     for (int item = item_lo; item < item_hi; ++item) {
-      const int tile = item / n_chunks;
+      const int vt = item / n_chunks;
+      const int tile = kMode == 0 ? vt : vt / NH;
       if (tile != staged_tile) {
         mbar_wait(a_full, it & 1u);
         ++it;
         staged_tile = tile;
       }
       tc_fence_after();
-      for (int oi = 0; oi < oc; ++oi, ++ocount) {
+      for (int oi = 0; oi < oc * kHalvesPerItem; ++oi, ++ocount) {
         const uint32_t b = ocount & 1u;
         mbar_wait(&tmem_empty[b], ((ocount >> 1) + 1) & 1u);
         tc_fence_after();
@@ -291,9 +313,9 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
           if (lane == 0) {
             const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes);
             const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
-            const uint32_t d = tmem + b * 2 * F, dc = d + F;
-            // one N = 2F MMA multiplies a_hi with the adjacent [b_hi; b_lo] images (main | correction columns), one
-            // N = F MMA adds a_lo * b_hi to the correction columns; each K step is 16 halves = 32 bytes of the row
+            const uint32_t d = tmem + b * 256, dc = d + 128;
+            // one N = 256 MMA multiplies a_hi with the adjacent [b_hi; b_lo] images (main | correction columns), one
+            // N = 128 MMA adds a_lo * b_hi to the correction columns; each K step is 16 halves = 32 bytes of the row
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
@@ -307,7 +329,8 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
         }
       }
       // last item of this atom tile: the activation tile may be overwritten once these MMAs are done
-      if ((item + 1 == item_hi || (item + 1) / n_chunks != tile) && lane == 0) umma_commit(a_free);
+      const int next_tile = item + 1 == item_hi ? -1 : (kMode == 0 ? (item + 1) / n_chunks : (item + 1) / n_chunks / NH);
+      if (next_tile != tile && lane == 0) umma_commit(a_free);
       __syncwarp();
     }
   }
@@ -324,27 +347,35 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
 using namespace cgat;
 
 namespace {
+template <int F, int kMode>
+int launch_hyper16_f(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
+                     const float* w_packed, float* y_out, int64_t n_atoms, cudaStream_t stream, float* scale_amax) {
+  using Cfg = Hyper16Cfg<F>;
+  static bool configured = false;
+  if (!configured) {
+    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_f16_kernel<F, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  const int oc = hyper_chunk(n_atoms, F);
+  const int grid = hyper_grid(n_atoms, F, kMode);
+  hyper_rowdot_f16_kernel<F, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, F),
+      reinterpret_cast<unsigned int*>(scale_amax));
+  return check_launch(kMode == 0 ? "hyper_rowdot_f16_kernel" : "hyper_rowscale_f16_kernel");
+}
+
 template <int kMode>
 int launch_hyper16(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
                    const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream,
                    float* scale_amax = nullptr) {
-  using Cfg = Hyper16Cfg<128>;
   if (n_atoms <= 0) return 0;
-  if (f != 128) return fail(-2, "cgat_hyper_*_f16: only F = 128 is instantiated");
+  if (f != 128 && f != 256) return fail(-2, "cgat_hyper_*_f16: instantiated for F = 128 and F = 256");
   if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_*_f16: too many atoms");
   if (w_bias && (reinterpret_cast<uintptr_t>(w_bias) & 15)) return fail(-2, "cgat_hyper_*_f16: w_bias must be 16-byte aligned");
-  static bool configured = false;
-  if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_f16_kernel<128, kMode>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   Cfg::kSmemBytes));
-    configured = true;
-  }
-  const int oc = hyper_chunk(n_atoms, f);
-  const int grid = hyper_grid(n_atoms, f);
-  hyper_rowdot_f16_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f),
-      reinterpret_cast<unsigned int*>(scale_amax));
-  return check_launch(kMode == 0 ? "hyper_rowdot_f16_kernel" : "hyper_rowscale_f16_kernel");
+  if (f == 128)
+    return launch_hyper16_f<128, kMode>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, stream, scale_amax);
+  return launch_hyper16_f<256, kMode>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, stream, scale_amax);
 }
 }  // namespace
 

@@ -348,7 +348,7 @@ int launch_hyper_impl(const float* z, const float* y_in, const float* e_term, co
     configured = true;
   }
   const int oc = hyper_chunk(n_atoms, f);
-  const int grid = hyper_grid(n_atoms, f);
+  const int grid = hyper_grid(n_atoms, f, kMode);
   hyper_rowdot_fwd_kernel<128, kMode, kTS><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
       z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f));
   return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");

@@ -24,7 +24,10 @@ __global__ void pack_kmajor_kernel(const float* __restrict__ w, int64_t ld, int 
       if (gr < rows && gk + j < k) {
         if (transpose == 0) x = w[(int64_t)gr * ld + gk + j];
         else if (transpose == 1) x = w[(int64_t)(gk + j) * ld + gr];
-        else x = w[((int64_t)rt * kPackRows + gk + j) * ld + r];  // 2: transpose inside each 128 x 128 block
+        else {  // 2: transpose inside each k x k block: packed row (o, c) holds column c of block o
+          const int64_t o = ((int64_t)rt * kPackRows) / k, c0 = ((int64_t)rt * kPackRows) % k;
+          x = w[(o * k + gk + j) * ld + c0 + r];
+        }
       }
       v[j] = x;
     }
@@ -52,7 +55,10 @@ __global__ void pack_kmajor_f16_kernel(const float* __restrict__ w, int64_t ld, 
       if (gr < rows && gk + j < k) {
         if (transpose == 0) x = w[(int64_t)gr * ld + gk + j];
         else if (transpose == 1) x = w[(int64_t)(gk + j) * ld + gr];
-        else x = w[((int64_t)rt * kPackRows + gk + j) * ld + r];  // 2: transpose inside each 128 x 128 block
+        else {  // 2: transpose inside each k x k block: packed row (o, c) holds column c of block o
+          const int64_t o = ((int64_t)rt * kPackRows) / k, c0 = ((int64_t)rt * kPackRows) % k;
+          x = w[(o * k + gk + j) * ld + c0 + r];
+        }
       }
       v[j] = x * pre_scale;
     }
@@ -72,12 +78,12 @@ using namespace cgat;
 extern "C" int64_t cgat_packed_floats(int64_t rows, int64_t k) { return tc::packed_floats(rows, k); }
 
 // w: [rows x k] (transpose=0, leading dimension ld), its transpose stored as [k x rows] (transpose=1), or
-// a stack of 128 x 128 blocks each of which is transposed (transpose=2; needs k == 128, rows % 128 == 0).
+// a stack of k x k blocks each of which is transposed (transpose=2; needs k % 128 == 0, rows % k == 0).
 extern "C" int cgat_pack_kmajor(const float* w, int64_t ld, int64_t rows, int64_t k, int32_t transpose, float* out,
                                 void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows <= 0 || k <= 0) return 0;
-  if (transpose == 2 && (k != tc::kPackRows || rows % tc::kPackRows)) return fail(-2, "cgat_pack_kmajor: block transpose needs 128 x 128 blocks");
+  if (transpose == 2 && (k % tc::kPackRows || rows % k)) return fail(-2, "cgat_pack_kmajor: block transpose needs k x k blocks, k a multiple of 128");
   dim3 grid((unsigned)ceil_div(k, tc::kPackChunk), (unsigned)ceil_div(rows, tc::kPackRows));
   pack_kmajor_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, out);
   return check_launch("pack_kmajor_kernel");
@@ -91,7 +97,7 @@ extern "C" int cgat_pack_kmajor_f16s(const float* w, int64_t ld, int64_t rows, i
                                      float pre_scale, float lo_scale, float* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (rows <= 0 || k <= 0) return 0;
-  if (transpose == 2 && (k != tc::kPackRows || rows % tc::kPackRows)) return fail(-2, "cgat_pack_kmajor_f16: block transpose needs 128 x 128 blocks");
+  if (transpose == 2 && (k % tc::kPackRows || rows % k)) return fail(-2, "cgat_pack_kmajor_f16: block transpose needs k x k blocks, k a multiple of 128");
   dim3 grid((unsigned)ceil_div(k, tc::kPackChunk16), (unsigned)ceil_div(rows, tc::kPackRows));
   pack_kmajor_f16_kernel<<<grid, 256, 0, stream>>>(w, ld, (int)rows, (int)k, transpose, pre_scale, lo_scale, out);
   return check_launch("pack_kmajor_f16_kernel");

@@ -412,7 +412,7 @@ class _HyperLinear(torch.autograd.Function):
             g_z = g_z + gemm3x(g, weight[ff:].t().contiguous())
         # weight gradient: dW[o*F+i,k] = sum_n g[n,o] y[n,i] z[n,k] — contraction over atoms, outer product on the fly
         lib = _lib.load()
-        splits = int(lib.cgat_hyper_wgrad_splits(n))
+        splits = int(lib.cgat_hyper_wgrad_splits(n)) if f == 128 else 1     # F = 256: 512 CTAs without an atom split
         wpart = torch.empty((splits, ff, f), dtype=torch.float32, device=y.device)
         if f16_grad:
             _lib.call("cgat_hyper_wgrad_f16", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(g_amax), _lib.ptr(wpart),
@@ -437,7 +437,10 @@ def hyper_linear(z, weight, bias, y, out_ch, e=None):
     (reference HyperLinear.forward + BatchLinear.forward, CGAT/Hypernetworksmp.py:243-254, 205-209).
     `e`: weight[out*in:] z + bias[out*in:] if hyper_trunks has already computed it (fused path only)."""
     in_ch = y.shape[1]
-    if _FUSED and z.is_cuda and in_ch == 128 and out_ch == 128 and z.shape[1] == 128:
+    # fused kernels: F = 128 (tf32 or f16 operands) and F = 256 (BASELINE.json configs[3]; f16 operand kernels only)
+    fused = (_FUSED and z.is_cuda and in_ch == out_ch == z.shape[1]
+             and (in_ch == 128 or (in_ch == 256 and _F16X3 and _F16X3_GRAD)))
+    if fused:
         return _HyperLinear.apply(z, weight, bias, y, e, packed_kmajor(weight, in_ch * out_ch, f16=_F16X3),
                                   packed_kmajor(weight, in_ch * out_ch, 2, f16=_F16X3) if torch.is_grad_enabled()
                                   else None, _F16X3)

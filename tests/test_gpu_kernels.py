@@ -106,6 +106,35 @@ def test_library_loaded_and_counting():
     assert _lib.launch_count() > before
 
 
+@pytest.mark.parametrize("n", [1, 130, 700, 3000])
+def test_hyper_linear_fused_f256(n):
+    """The F = 256 instantiation of the fused hyper-linear kernels (BASELINE.json configs[3]: hidden 256): forward,
+    both activation gradients (two 128-column halves per predicted-weight row) and the weight gradient (one N = 256
+    accumulator per (output channel, row half)) against fp64."""
+    f = 256
+    g = torch.Generator().manual_seed(n)
+    z = torch.tanh(torch.randn(n, f, generator=g))
+    y = torch.randn(n, f, generator=g)
+    w = torch.randn(f * f + f, f, generator=g) * 0.0125 * 0.7
+    b = torch.randn(f * f + f, generator=g) * 0.09
+    zd, yd, wd, bd = (t.double().requires_grad_(True) for t in (z, y, w, b))
+    p = zd @ wd.t() + bd
+    ref = torch.einsum("noi,ni->no", p[:, : f * f].view(n, f, f), yd) + p[:, f * f:]
+    gw = torch.randn(n, f, generator=g).double() * 1e-3          # a realistically small upstream gradient
+    (ref * gw).sum().backward()
+    zc, yc, wc, bc = (t.to(DEV).requires_grad_(True) for t in (z, y, w, b))
+    before = _lib.launch_count()
+    out = ops.hyper_linear(zc, wc, bc, yc, f)
+    (out * gw.float().to(DEV)).sum().backward()
+    assert _lib.launch_count() - before >= 6, "the fused F = 256 kernels did not run"
+    assert_close(out.detach(), ref.detach(), "hyper fwd", atol=4e-5, rtol=1e-4)
+    sc = gw.abs().max().item()
+    assert_close(zc.grad, zd.grad, "g_z", atol=1e-4 * sc, rtol=1e-3)
+    assert_close(yc.grad, yd.grad, "g_y", atol=1e-4 * sc, rtol=1e-3)
+    assert_close(wc.grad, wd.grad, "g_w", atol=1e-5 * wd.grad.abs().max().item() + 1e-4 * sc, rtol=1e-3)
+    assert_close(bc.grad, bd.grad, "g_b", atol=1e-5 * bd.grad.abs().max().item() + 1e-4 * sc, rtol=1e-3)
+
+
 @pytest.mark.parametrize("f16", [True, False], ids=["f16x3", "tf32x3"])
 @pytest.mark.parametrize("n", [1, 119, 128, 700, 5559])
 def test_hyper_linear_fused_fwd_bwd(n, f16, monkeypatch):
