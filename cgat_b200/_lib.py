@@ -44,6 +44,7 @@ SIGNATURES = {
     "cgat_edge_attn_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,
                                               _I32, _I32, _F32, _P]),
     "cgat_edge_attn_bwd_prep_f16": (ctypes.c_int, [_P] * 19 + [_I64, _I64, _I32, _I32, _I32, _F32, _P]),
+    "cgat_edge_attn_wgrad_f16_splits": (_I32, [_I32, _I32, _I32]),
     "cgat_edge_attn_wgrad_f16": (ctypes.c_int, [_P] * 9 + [_I64, _I32, _I32, _I32, _P]),
     "cgat_hyper_rowdot_fwd_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowscale_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),

@@ -52,6 +52,7 @@ struct DgradArgs {
   const float* dz_amax;    // kF16: device float max |d_gate|, |d_msg| (power-of-two range of the gradient operand)
   int64_t ldg;
   int col_off, n_atoms, n_edges, heads, hd, n_ranks;
+  int f;                   // channels per head (128; the f16 d_pre form also 256)
 };
 
 __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int64_t key) {
@@ -90,7 +91,7 @@ __global__ void __launch_bounds__(kDThreads, 1) edge_dgrad_kernel(const DgradArg
   const int nhalf = (hd + 127) / 128;   // M tiles of 128 hidden units per head
   const int n_items = 2 * H * nhalf;
   constexpr int kChunkF = kF16 ? kPackChunk16 : kPackChunk;   // channels per pipeline stage
-  constexpr int kcf = kBF / kChunkF;    // K chunks of the dgrad contraction (over channels)
+  const int kcf = g.f / kChunkF;        // K chunks of the dgrad contraction (over channels)
   float s_scale = 1.f, s_inv = 1.f;
   if (kF16) {
     const float amax = __ldg(g.dz_amax);
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(kDThreads, 1) edge_dgrad_kernel(const DgradArg
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int r = (pt + kBProducers * j) >> 3;
-          rowoff[j] = (r < nv) ? ((int64_t)mt[kBT + r] * H + h) * kBF : -1;  // padding rows are staged as zeros
+          rowoff[j] = (r < nv) ? ((int64_t)mt[kBT + r] * H + h) * g.f : -1;  // padding rows are staged as zeros
         }
         // the dZ rows of K chunk kc+1 are requested before this thread waits for the stage of chunk kc, so the
         // L2 / HBM latency of the loads overlaps the wait and the conversion (was: load -> wait for data -> convert)
@@ -774,7 +775,7 @@ extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, con
   }
   if (d_pre && row) return fail(-2, "cgat_edge_attn_dgrad: d_pre needs the identity edge order (row == NULL)");
   DgradArgs a{d_gate, d_msg, signs, segptr, seg, row, rnk, wt_a_packed, wt_m_packed, G, d_rank, d_pre, nullptr, ldg,
-              col_off, (int)n_atoms, (int)n_edges, heads, hd, n_ranks};
+              col_off, (int)n_atoms, (int)n_edges, heads, hd, n_ranks, kBF};
   if (d_pre) edge_dgrad_kernel<false, true><<<cgat_edge_attn_dgrad_grid(n_edges), kDThreads, kBSmemBytes, stream>>>(a);
   else edge_dgrad_kernel<false, false><<<cgat_edge_attn_dgrad_grid(n_edges), kDThreads, kBSmemBytes, stream>>>(a);
   return check_launch("edge_dgrad_kernel");
@@ -787,9 +788,10 @@ extern "C" int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg,
                                         const float* wt_m_packed, const float* dz_amax, float* d_pre, int64_t n_atoms,
                                         int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (f != kBF) return fail(-2, "cgat_edge_attn_dgrad_f16: only F = 128 is instantiated");
-  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 127))
-    return fail(-2, "cgat_edge_attn_dgrad_f16: heads must be in [1,8] and the hidden width a multiple of 128");
+  if (f != kBF && f != 2 * kBF) return fail(-2, "cgat_edge_attn_dgrad_f16: F must be 128 or 256");
+  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 31))
+    return fail(-2, "cgat_edge_attn_dgrad_f16: heads must be in [1,8] and the hidden width a multiple of 32 (W2^T packed "
+                    "with ceil(hd / 128) * 128 rows per head)");
   if (!d_pre || !dz_amax) return fail(-2, "cgat_edge_attn_dgrad_f16: d_pre and dz_amax are required");
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   static bool configured = false;
@@ -798,7 +800,7 @@ extern "C" int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg,
     configured = true;
   }
   DgradArgs a{d_gate, d_msg, signs, segptr, seg, nullptr, nullptr, wt_a_packed, wt_m_packed, nullptr, nullptr, d_pre,
-              dz_amax, 0, 0, (int)n_atoms, (int)n_edges, heads, hd, 1};
+              dz_amax, 0, 0, (int)n_atoms, (int)n_edges, heads, hd, 1, f};
   edge_dgrad_kernel<true, true><<<cgat_edge_attn_dgrad_grid(n_edges), kDThreads, kBSmemBytes, stream>>>(a);
   return check_launch("edge_dgrad_f16_kernel");
 }

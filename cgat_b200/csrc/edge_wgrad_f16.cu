@@ -41,6 +41,7 @@ struct WArgs {
   const float* dz_amax;   // device float: max |dZ| over both nets
   float* out;             // (n_split, 2, H, F, Hd) partial dW2
   int n_edges, heads, hd, n_split;
+  int f, n_ch, n_kh;      // channels per head; 128-channel blocks per head; 256-wide blocks of the hidden units
 };
 
 __device__ __forceinline__ float lrelu_w(float x) { return x > 0.f ? x : 0.01f * x; }
@@ -58,8 +59,11 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int H = g.heads, hd = g.hd, hhd = H * hd;
+  // item = (net, head, 128-channel block, 256-hidden-unit block): one 128 x 256 accumulator tile of dW2[net, head]
   const int item = blockIdx.x / g.n_split, split = blockIdx.x % g.n_split;
-  const int net = item / H, h = item % H;
+  const int kh = item % g.n_kh, chb = (item / g.n_kh) % g.n_ch, h = (item / (g.n_kh * g.n_ch)) % H;
+  const int net = item / (g.n_kh * g.n_ch * H);
+  const int F = g.f, c0 = chb * 128, k0 = kh * 256;
   const int e_lo = (int)((int64_t)g.n_edges * split / g.n_split), e_hi = (int)((int64_t)g.n_edges * (split + 1) / g.n_split);
   const int n_chunks = (e_hi - e_lo + kWRows - 1) / kWRows;
   const int64_t ldp = 4 * (int64_t)hhd, ldt = 2 * (int64_t)hhd;
@@ -88,7 +92,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
     const int c = warp * 32 + lane;
     mbar_wait(accum, 0);
     tc_fence_after();
-    float* dst = g.out + ((((int64_t)split * 2 + net) * H + h) * kWF + c) * hd;
+    float* dst = g.out + ((((int64_t)split * 2 + net) * H + h) * F + c0 + c) * hd + k0;
 #pragma unroll 1
     for (int cc = 0; cc < 8; ++cc) {
       float v[32], w[32];
@@ -97,7 +101,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (cc * 32 + j < hd) dst[cc * 32 + j] = n_chunks > 0 ? fmaf(w[j], kF16LoInv, v[j]) * s_inv : 0.f;
+        if (k0 + cc * 32 + j < hd) dst[cc * 32 + j] = n_chunks > 0 ? fmaf(w[j], kF16LoInv, v[j]) * s_inv : 0.f;
     }
     tc_fence_before();
   } else if (warp < kWMmaWarp) {
@@ -131,7 +135,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
       for (int j = 0; j < 4; ++j) {
         const int idx = pl + kWGroup * j, r = idx >> 5, q = idx & 31;
         a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nv) a[j] = __ldg(reinterpret_cast<const float4*>(dz + ((int64_t)(e0 + r) * H + h) * kWF + q * 4));
+        if (r < nv) a[j] = __ldg(reinterpret_cast<const float4*>(dz + ((int64_t)(e0 + r) * H + h) * F + c0 + q * 4));
       }
       float4 x[8];
 #pragma unroll
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
         const int idx = pl + kWGroup * j, r = idx >> 6, q = idx & 63;
         const int d = mt[r];
         x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d >= 0 && q * 4 < hd) {
-          const int col = net * hhd + h * hd + q * 4;
+        if (d >= 0 && k0 + q * 4 < hd) {
+          const int col = net * hhd + h * hd + k0 + q * 4;
           const float4 pd = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)d * ldp + col));
           const float4 ps = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)mt[32 + r] * ldp + 2 * hhd + col));
           const float4 te = __ldg(reinterpret_cast<const float4*>(g.T + (int64_t)mt[64 + r] * ldt + col));
@@ -212,6 +216,13 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
 
 using namespace cgat;
 
+// number of edge ranges (= partial results) of cgat_edge_attn_wgrad_f16: about one CTA per SM over all accumulator tiles
+extern "C" int32_t cgat_edge_attn_wgrad_f16_splits(int32_t heads, int32_t f, int32_t hd) {
+  const int items = 2 * heads * (f / kWF) * ((hd + 255) / 256);
+  const int s = kNumSMs / (items > 0 ? items : 1);
+  return s < 1 ? 1 : s;
+}
+
 // cgat_edge_attn_wgrad on kind::f16 passes: same arguments and result layout plus dz_amax, the device float that
 // cgat_edge_attn_bwd_prep[_f16] leaves behind (max |d_gate|, |d_msg|).
 extern "C" int cgat_edge_attn_wgrad_f16(const float* P, const float* T, const int32_t* src, const int32_t* dst,
@@ -219,9 +230,9 @@ extern "C" int cgat_edge_attn_wgrad_f16(const float* P, const float* T, const in
                                         const float* dz_amax, float* out, int64_t n_edges, int32_t heads, int32_t f,
                                         int32_t hd, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (f != kWF) return fail(-2, "cgat_edge_attn_wgrad_f16: only F = 128 is instantiated");
-  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 15) || hd > 256)
-    return fail(-2, "cgat_edge_attn_wgrad_f16: hidden width must be a multiple of 16, at most 256");
+  if (f != kWF && f != 2 * kWF) return fail(-2, "cgat_edge_attn_wgrad_f16: F must be 128 or 256");
+  if (heads < 1 || heads > 8 || hd <= 0 || (hd & 3) || hd > 512)
+    return fail(-2, "cgat_edge_attn_wgrad_f16: hidden width must be a multiple of 4, at most 512");
   if (dz_amax == nullptr) return fail(-2, "cgat_edge_attn_wgrad_f16: dz_amax is required");
   if (n_edges <= 0) return 0;
   static bool configured = false;
@@ -229,8 +240,9 @@ extern "C" int cgat_edge_attn_wgrad_f16(const float* P, const float* T, const in
     CGAT_CUDA(cudaFuncSetAttribute(edge_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
     configured = true;
   }
-  const int n_split = cgat_edge_attn_wgrad_splits(heads);
-  WArgs a{P, T, src, dst, rank, d_gate, d_msg, dz_amax, out, (int)n_edges, heads, hd, n_split};
-  edge_wgrad_f16_kernel<<<2 * heads * n_split, kWThreads, kWSmem, stream>>>(a);
+  const int n_split = cgat_edge_attn_wgrad_f16_splits(heads, f, hd);
+  const int n_ch = f / kWF, n_kh = (hd + 255) / 256;
+  WArgs a{P, T, src, dst, rank, d_gate, d_msg, dz_amax, out, (int)n_edges, heads, hd, n_split, f, n_ch, n_kh};
+  edge_wgrad_f16_kernel<<<2 * heads * n_ch * n_kh * n_split, kWThreads, kWSmem, stream>>>(a);
   return check_launch("edge_wgrad_f16_kernel");
 }

@@ -576,38 +576,66 @@ def hyper_trunks(h, layers, tails):
 
 
 def _w2_transposed_packed(w2, heads, f16=False):
-    """Packed W2^T per head, (H*Hd, F): row h*Hd+k, col c = W2[h*F+c, k] — the A operand of the dgrad MMAs
-    (tf32 hi/lo images, or fp16 hi / 2^11-scaled lo images for cgat_edge_attn_dgrad_f16)."""
+    """Packed W2^T per head, (H*Hd128, F): row h*Hd128+k, col c = W2[h*F+c, k] — the A operand of the dgrad MMAs
+    (tf32 hi/lo images, or fp16 hi / 2^11-scaled lo images for cgat_edge_attn_dgrad_f16).  Hd128 = the hidden width
+    rounded up to whole 128-row tiles (zero rows), so that every head starts on a tile boundary."""
     cache = w2.__dict__.setdefault("_cgat_packed", {})
     tag = "w2t16" if f16 else "w2t"
     hit = cache.get(tag)
     if hit is not None and hit[0] == (w2._version, _pack_epoch) and hit[2] == w2.data_ptr():
         return hit[1]
     hf, hd = w2.shape[0], w2.shape[1]
-    wt = w2.detach().view(heads, hf // heads, hd).transpose(1, 2).reshape(heads * hd, hf // heads).contiguous()
+    hd128 = -(-hd // 128) * 128
+    wt = w2.detach().view(heads, hf // heads, hd).transpose(1, 2)                       # (H, Hd, F)
+    if hd128 != hd:
+        wt = torch.nn.functional.pad(wt, (0, 0, 0, hd128 - hd))
+    wt = wt.reshape(heads * hd128, hf // heads).contiguous()
     buf = packed_kmajor(wt, f16=f16)   # wt is a temporary: its packed image is a fresh buffer owned by this cache entry
     cache[tag] = ((w2._version, _pack_epoch), buf, w2.data_ptr())
     return buf
 
 
-def _first_layer_operands(w1a, w1m, b1a, b1m, f, fe):
+def _pad_heads(t, heads, hd, hd_pad):
+    """(H*hd, ...) -> (H*hd_pad, ...): zero rows appended to every head's block."""
+    if hd_pad == hd:
+        return t
+    v = t.reshape(heads, hd, *t.shape[1:])
+    pad = [0, 0] * (v.dim() - 2) + [0, hd_pad - hd]
+    return torch.nn.functional.pad(v, pad).reshape(heads * hd_pad, *t.shape[1:])
+
+
+def _unpad_heads(t, blocks, hd, hd_pad):
+    """(blocks*hd_pad, ...) -> (blocks*hd, ...): the inverse of _pad_heads over `blocks` consecutive head blocks."""
+    if hd_pad == hd:
+        return t
+    return t.reshape(blocks, hd_pad, *t.shape[1:])[:, :hd].reshape(blocks * hd, *t.shape[1:])
+
+
+def _first_layer_operands(w1a, w1m, b1a, b1m, f, fe, heads, hd_pad):
     """Regrouped first-layer weights of the gate / message MLPs: per-atom block (4*HHd, F) =
-    [W1A_i; W1M_i; W1A_j; W1M_j] (+ its packed image), per-rank block (2*HHd, Fe) = [W1A_e; W1M_e] and the
-    concatenated bias.  Cached on the weight and keyed by the autograd versions, so screening inference builds
-    them once and training once per optimizer step."""
-    key = (_pack_epoch,) + tuple((t._version, t.data_ptr()) for t in (w1a, w1m, b1a, b1m))
+    [W1A_i; W1M_i; W1A_j; W1M_j] (+ its packed image when F <= 128), per-rank block (2*HHd, Fe) = [W1A_e; W1M_e] and
+    the concatenated bias, with every head's hidden units zero-padded to hd_pad (a multiple of 64: the f16 kernels
+    stage 64 hidden units per pipeline step; padded units have zero weights and bias, hence zero activation).
+    Cached on the weight and keyed by the autograd versions, so screening inference builds them once and training
+    once per optimizer step."""
+    key = (_pack_epoch, hd_pad) + tuple((t._version, t.data_ptr()) for t in (w1a, w1m, b1a, b1m))
     cache = w1a.__dict__.setdefault("_cgat_first_layer", {})
     if cache.get("key") == key:
         return cache["val"]
-    hhd = w1a.shape[0]
-    w1a2, w1m2 = w1a.detach().view(hhd, -1), w1m.detach().view(hhd, -1)
-    w_atom = torch.cat([w1a2[:, :f], w1m2[:, :f], w1a2[:, f + fe:], w1m2[:, f + fe:]], dim=0)       # (4*HHd, F)
-    w_rank = torch.cat([w1a2[:, f:f + fe], w1m2[:, f:f + fe]], dim=0)                               # (2*HHd, Fe)
-    b1 = torch.cat([b1a.detach(), b1m.detach()])
-    lib = _lib.load()
-    packed = torch.empty(int(lib.cgat_packed_floats(4 * hhd, f)), dtype=torch.float32, device=w1a.device)
-    _lib.call("cgat_pack_kmajor", _lib.ptr(w_atom), w_atom.stride(0), 4 * hhd, f, 0, _lib.ptr(packed), _lib.stream(),
-              work=dict(key="pack_kmajor", bound="hbm", bytes=12.0 * 4 * hhd * f))
+    hhd0 = w1a.shape[0]
+    hd = hhd0 // heads
+    w1a2 = _pad_heads(w1a.detach().view(hhd0, -1), heads, hd, hd_pad)
+    w1m2 = _pad_heads(w1m.detach().view(hhd0, -1), heads, hd, hd_pad)
+    hhd = heads * hd_pad
+    w_atom = torch.cat([w1a2[:, :f], w1m2[:, :f], w1a2[:, f + fe:], w1m2[:, f + fe:]], dim=0).contiguous()   # (4*HHd, F)
+    w_rank = torch.cat([w1a2[:, f:f + fe], w1m2[:, f:f + fe]], dim=0).contiguous()                         # (2*HHd, Fe)
+    b1 = torch.cat([_pad_heads(b1a.detach(), heads, hd, hd_pad), _pad_heads(b1m.detach(), heads, hd, hd_pad)])
+    packed = None
+    if f <= 128:
+        lib = _lib.load()
+        packed = torch.empty(int(lib.cgat_packed_floats(4 * hhd, f)), dtype=torch.float32, device=w1a.device)
+        _lib.call("cgat_pack_kmajor", _lib.ptr(w_atom), w_atom.stride(0), 4 * hhd, f, 0, _lib.ptr(packed), _lib.stream(),
+                  work=dict(key="pack_kmajor", bound="hbm", bytes=12.0 * 4 * hhd * f))
     cache["key"], cache["val"] = key, (w_atom, packed, w_rank, b1, w_atom.t().contiguous())
     return cache["val"]
 
@@ -616,20 +644,23 @@ class _EdgeAttentionFused(torch.autograd.Function):
     """Forward: per-atom / per-rank first-layer projections (cgat_gemm3x_nt_res / cgat_gemm3x_nt) + the fused
     gather / second-layer MMA / segmented-softmax kernel (cgat_edge_attn_fwd[_f16]).  No per-edge tensor is written.
     Backward: cgat_edge_attn_bwd_prep[_f16] (per-edge dL/da, dL/dv, LeakyReLU sign masks and the second-layer bias
-    gradients), cgat_edge_attn_dgrad (per-edge dL/d pre-activation), cgat_edge_attn_reduce (its per-destination /
-    per-source / per-rank sums), cgat_edge_attn_wgrad, and the first-layer products on cgat_gemm3x_nt_splitk /
-    cgat_gemm3x_tn.  Deterministic, atomic-free."""
+    gradients), cgat_edge_attn_dgrad[_f16] (per-edge dL/d pre-activation), cgat_edge_attn_reduce (its per-destination /
+    per-source / per-rank sums), cgat_edge_attn_wgrad[_f16], and the first-layer products on cgat_gemm3x_nt_splitk /
+    cgat_gemm3x_tn.  Deterministic, atomic-free.  `hd_pad`: the hidden width every kernel sees (hidden units of a
+    head zero-padded to a multiple of 64 on the f16 path: 426 -> 448 for BASELINE.json configs[3])."""
 
     @staticmethod
-    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads, f16):
+    def forward(ctx, x, edge_table, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, w2a_packed, w2m_packed, plan, heads, f16,
+                hd_pad):
         x, edge_table = _f32c(x), _f32c(edge_table)
         ctx.f16 = f16
         n, f = x.shape
         fe = edge_table.shape[1]
-        hhd = w1a.shape[0]
-        hd = hhd // heads
-        w_atom, w_atom_packed, w_rank, b1, w_atom_t = _first_layer_operands(w1a, w1m, b1a, b1m, f, fe)
-        P = gemm3x_res(x, w_atom_packed, 4 * hhd)                                                    # (N, 4*HHd)
+        hd = w1a.shape[0] // heads
+        hhd = heads * hd_pad
+        w_atom, w_atom_packed, w_rank, b1, w_atom_t = _first_layer_operands(w1a, w1m, b1a, b1m, f, fe, heads, hd_pad)
+        # (N, 4*HHd): K <= 128 on the resident-tile kernel, wider inputs on the plain 3-pass GEMM
+        P = gemm3x_res(x, w_atom_packed, 4 * hhd) if w_atom_packed is not None else gemm3x(x, w_atom)
         T = gemm3x(edge_table, w_rank, b1)                                                           # (K+1, 2*HHd)
         train = any(ctx.needs_input_grad)
         out = torch.empty((n, heads, f), dtype=torch.float32, device=x.device)
@@ -641,7 +672,7 @@ class _EdgeAttentionFused(torch.autograd.Function):
                   _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed),
                   _lib.ptr(b2a), _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden),
-                  n, e, heads, f, hd, 1e-16, _lib.stream(),
+                  n, e, heads, f, hd_pad, 1e-16, _lib.stream(),
                   work=dict(key="edge_attn_fwd", bound="tensor", flops=2.0 * e * heads * hd * 2 * f,
                             bytes=4.0 * (e * (3 + 2 * 2 * hhd) + n * heads * f),
                             note="second MLP layer (E x Hd x F per head, gate+message) on tcgen05, "
@@ -649,20 +680,20 @@ class _EdgeAttentionFused(torch.autograd.Function):
         if train:
             ctx.save_for_backward(x, edge_table, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax,
                                   sden, w_atom_t, w_rank)
-            ctx.plan, ctx.heads = plan, heads
+            ctx.plan, ctx.heads, ctx.hd_pad = plan, heads, hd_pad
         return out
 
     @staticmethod
     def backward(ctx, g):
         (x, tab, w1a, w1m, w2a, w2m, b2a, b2m, w2a_packed, w2m_packed, P, T, out, smax, sden, w_atom_t,
          w_rank) = ctx.saved_tensors
-        plan, heads = ctx.plan, ctx.heads
+        plan, heads, hd_pad = ctx.plan, ctx.heads, ctx.hd_pad
         n, f = x.shape
         fe = tab.shape[1]
-        hhd = w1a.shape[0]
-        hd = hhd // heads
+        hd = w1a.shape[0] // heads          # the real hidden width; hd_pad is what the kernels see
+        hhd = heads * hd_pad
         e = plan.n_edges
-        kcn = (hd + 31) // 32
+        kcn = (hd_pad + 31) // 32
         dev = x.device
         lib = _lib.load()
         g = _f32c(g)
@@ -675,14 +706,18 @@ class _EdgeAttentionFused(torch.autograd.Function):
         # per-CTA column sums of d_msg | d_gate (the second-layer bias gradients) come out of the same kernel
         bsum = (torch.empty if e > 0 else torch.zeros)((int(lib.cgat_edge_attn_grid(e)), 2, heads, f),
                                                       dtype=torch.float32, device=dev)   # e == 0: no launch, no writes
-        # max |dL/da|, |dL/dv| (device float, zeroed by the kernel's wrapper): the range of the f16 weight-gradient operand
-        f16_grad = _F16X3_GRAD and hd % 128 == 0 and hd <= 256
+        # max |dL/da|, |dL/dv| (device float, zeroed by the kernel's wrapper): the range of the f16 gradient operands.
+        # The tf32 gradient kernels only exist for F = 128 and whole 128-unit hidden tiles.
+        f16_grad = ctx.f16 and _F16X3_GRAD and hd_pad <= 512
+        if not f16_grad and (f != 128 or hd_pad % 128 or hd_pad > 256):
+            raise _lib.CgatLibraryError("edge attention backward: this shape needs the f16 gradient kernels "
+                                        "(CGAT_B200_F16X3_EDGE=1, CGAT_B200_F16X3_GRAD=1)")
         dz_amax = torch.empty(1, dtype=torch.float32, device=dev) if f16_grad else None
         _lib.call("cgat_edge_attn_bwd_prep_f16" if ctx.f16 else "cgat_edge_attn_bwd_prep", _lib.ptr(P), _lib.ptr(T),
                   _lib.ptr(plan.rowptr), _lib.ptr(plan.src),
                   _lib.ptr(plan.dst), _lib.ptr(plan.rank), _lib.ptr(w2a_packed), _lib.ptr(w2m_packed), _lib.ptr(b2a),
                   _lib.ptr(b2m), _lib.ptr(out), _lib.ptr(smax), _lib.ptr(sden), _lib.ptr(g), _lib.ptr(d_gate),
-                  _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(bsum), _lib.ptr(dz_amax), n, e, heads, f, hd, 1e-16, st,
+                  _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(bsum), _lib.ptr(dz_amax), n, e, heads, f, hd_pad, 1e-16, st,
                   work=dict(key="edge_attn_bwd_prep", bound="tensor", flops=flops2))
         # 2. dgrad on the tensor cores -> per-edge d_pre, then its per-destination / per-source / per-rank sums
         #    (HBM-bound, cgat_edge_attn_reduce)
@@ -692,13 +727,13 @@ class _EdgeAttentionFused(torch.autograd.Function):
         if f16_grad:
             _lib.call("cgat_edge_attn_dgrad_f16", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs),
                       _lib.ptr(plan.rowptr), _lib.ptr(plan.dst), _lib.ptr(wt_a), _lib.ptr(wt_m), _lib.ptr(dz_amax),
-                      _lib.ptr(d_pre), n, e, heads, f, hd, st,
+                      _lib.ptr(d_pre), n, e, heads, f, hd_pad, st,
                       work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2,
                                 note="f16x3, gradient operand scaled by 2^k"))
         else:
             _lib.call("cgat_edge_attn_dgrad", _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(signs), _lib.ptr(plan.rowptr),
                       _lib.ptr(plan.dst), None, None, _lib.ptr(wt_a), _lib.ptr(wt_m), None, 4 * hhd, 0, None,
-                      n_ranks, _lib.ptr(d_pre), n, e, heads, f, hd, st,
+                      n_ranks, _lib.ptr(d_pre), n, e, heads, f, hd_pad, st,
                       work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2))
         so = plan.by_source()
         chunks = int(lib.cgat_edge_attn_reduce_chunks(n))
@@ -713,31 +748,36 @@ class _EdgeAttentionFused(torch.autograd.Function):
         del d_pre
         d_t = sum_parts(d_rank)                                                     # (K+1, 2*HHd)
         # 3. second-layer weight / bias gradients
-        splits = int(lib.cgat_edge_attn_wgrad_splits(heads))
-        part = torch.empty((splits, 2, heads, f, hd), dtype=torch.float32, device=dev)
         if f16_grad:
+            splits = int(lib.cgat_edge_attn_wgrad_f16_splits(heads, f, hd_pad))
+            part = torch.empty((splits, 2, heads, f, hd_pad), dtype=torch.float32, device=dev)
             _lib.call("cgat_edge_attn_wgrad_f16", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
                       _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(dz_amax), _lib.ptr(part), e, heads,
-                      f, hd, st, work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2,
-                                           note="f16x3, gradient operand scaled by 2^k"))
+                      f, hd_pad, st, work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2,
+                                               note="f16x3, gradient operand scaled by 2^k"))
         else:
+            splits = int(lib.cgat_edge_attn_wgrad_splits(heads))
+            part = torch.empty((splits, 2, heads, f, hd_pad), dtype=torch.float32, device=dev)
             _lib.call("cgat_edge_attn_wgrad", _lib.ptr(P), _lib.ptr(T), _lib.ptr(plan.src), _lib.ptr(plan.dst),
-                      _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(part), e, heads, f, hd, st,
+                      _lib.ptr(plan.rank), _lib.ptr(d_gate), _lib.ptr(d_msg), _lib.ptr(part), e, heads, f, hd_pad, st,
                       work=dict(key="edge_attn_wgrad", bound="tensor", flops=flops2))
-        d_w2 = sum_parts(part)
+        d_w2 = sum_parts(part)                                                      # (2, H, F, hd_pad)
+        if hd_pad != hd:
+            d_w2 = d_w2[..., :hd]
         g_w2a, g_w2m = d_w2[0].reshape(w2a.shape), d_w2[1].reshape(w2m.shape)
         g_b2 = sum_parts(bsum)
         g_b2m, g_b2a = g_b2[0].reshape(-1), g_b2[1].reshape(-1)
-        # 4. first layer: P = x w_atom^T, T = tab w_rank^T + b1
+        # 4. first layer: P = x w_atom^T, T = tab w_rank^T + b1 (gradients of the zero-padded hidden units are dropped)
         g_x = gemm3x_splitk(d_p, w_atom_t)
-        g_watom = gemm3x_tn(d_p, x)                                                 # (4*HHd, F)
+        g_watom = _unpad_heads(gemm3x_tn(d_p, x), 4 * heads, hd, hd_pad)            # (4*H*Hd, F)
         g_tab = d_t @ w_rank
-        g_wrank = d_t.t() @ tab                                                     # (2*HHd, Fe)
-        g_b1 = d_t.sum(dim=0)
-        g_w1a = torch.cat([g_watom[:hhd], g_wrank[:hhd], g_watom[2 * hhd:3 * hhd]], dim=1).reshape(w1a.shape)
-        g_w1m = torch.cat([g_watom[hhd:2 * hhd], g_wrank[hhd:], g_watom[3 * hhd:]], dim=1).reshape(w1m.shape)
-        return (g_x, g_tab, g_w1a, g_b1[:hhd], g_w2a, g_b2a, g_w1m, g_b1[hhd:], g_w2m, g_b2m, None, None, None, None,
-                None)
+        g_wrank = _unpad_heads(d_t.t() @ tab, 2 * heads, hd, hd_pad)                # (2*H*Hd, Fe)
+        g_b1 = _unpad_heads(d_t.sum(dim=0), 2 * heads, hd, hd_pad)
+        hh = heads * hd
+        g_w1a = torch.cat([g_watom[:hh], g_wrank[:hh], g_watom[2 * hh:3 * hh]], dim=1).reshape(w1a.shape)
+        g_w1m = torch.cat([g_watom[hh:2 * hh], g_wrank[hh:], g_watom[3 * hh:]], dim=1).reshape(w1m.shape)
+        return (g_x, g_tab, g_w1a, g_b1[:hh], g_w2a, g_b2a, g_w1m, g_b1[hh:], g_w2m, g_b2m, None, None, None, None,
+                None, None)
 
 
 def edge_attention_heads_unfused(x, edge_table, plan, w1a, b1a, w2a, b2a, w1m, b1m, w2m, b2m, heads):
@@ -768,16 +808,23 @@ def edge_attention(x, edge_table, plan, mh_a, mh_m, heads, edge_ids=None):
     the destination-sorted order; that variant runs the unfused formulation (the fused kernel gathers a per-rank table)."""
     f = x.shape[1]
     hd = mh_a.hidden_dim
-    fused_ok = (_FUSED and edge_ids is None and x.is_cuda and f == 128 and mh_a.output_dim == f and mh_m.output_dim == f
-                and hd % 128 == 0 and hd <= 256 and heads <= 8 and edge_table.shape[1] % 4 == 0
-                and edge_table.shape[0] <= 32)
-    if fused_ok:
-        f16 = _F16X3_EDGE and hd % 64 == 0
+    base_ok = (_FUSED and edge_ids is None and x.is_cuda and mh_a.output_dim == f and mh_m.output_dim == f
+               and heads <= 8 and edge_table.shape[1] % 4 == 0 and edge_table.shape[0] <= 32)
+    # the original instantiation: F = 128, whole 128-unit hidden tiles (tf32 kernels, or f16 forward + either backward)
+    small_ok = base_ok and f == 128 and hd % 128 == 0 and hd <= 256
+    # generalised f16 path (BASELINE.json configs[3]: F = 256, 8 heads, Hd = 426): F in {128, 256} run as F / 128
+    # virtual heads, hidden units zero-padded to a multiple of 64 (426 -> 448), gradient kernels on kind::f16 too
+    hd_pad = -(-hd // 64) * 64
+    wide_ok = (base_ok and _F16X3_EDGE and _F16X3_GRAD and f in (128, 256) and heads * (f // 128) <= 16
+               and hd_pad <= 512)
+    if small_ok or wide_ok:
+        f16 = (_F16X3_EDGE and hd % 64 == 0) if small_ok else True
         pk = dict(f16=True, pre_scale=_EDGE_W2_PRESCALE) if f16 else {}
         out = _EdgeAttentionFused.apply(x, edge_table, mh_a.fc_in.weight, mh_a.fc_in.bias, mh_a.fc_out.weight,
                                         mh_a.fc_out.bias, mh_m.fc_in.weight, mh_m.fc_in.bias, mh_m.fc_out.weight,
                                         mh_m.fc_out.bias, packed_kmajor(mh_a.fc_out.weight, **pk),
-                                        packed_kmajor(mh_m.fc_out.weight, **pk), plan, heads, f16)
+                                        packed_kmajor(mh_m.fc_out.weight, **pk), plan, heads, f16,
+                                        hd_pad if f16 else hd)
         return out.mean(dim=1)
     return edge_attention_unfused(x, edge_table, plan, mh_a.w_in(), mh_a.fc_in.bias, mh_a.w_out(), mh_a.fc_out.bias,
                                   mh_m.w_in(), mh_m.fc_in.bias, mh_m.w_out(), mh_m.fc_out.bias, heads, edge_ids)

@@ -264,6 +264,7 @@ int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, con
                          int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream);
 /* kind::f16 form (twice the tensor rate, 4 x 48 KB stages, two alternating producer groups): d_gate / d_msg are
  * multiplied by a power of two derived from dz_amax[0] (left by cgat_edge_attn_bwd_prep) and the result divided by it. */
+int32_t cgat_edge_attn_wgrad_f16_splits(int32_t heads, int32_t f, int32_t hd);   /* partial results it writes */
 int cgat_edge_attn_wgrad_f16(const float* P, const float* T, const int32_t* src, const int32_t* dst,
                              const int32_t* rank, const float* d_gate, const float* d_msg, const float* dz_amax,
                              float* out, int64_t n_edges, int32_t heads, int32_t f, int32_t hd, void* stream);

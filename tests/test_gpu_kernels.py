@@ -234,9 +234,24 @@ def test_edge_attention_fused_backward_all_grads(n_cry, k, heads, lo, hi, f16, m
     """Fused edge-attention backward (bwd_prep + dgrad x2 + wgrad + first-layer GEMMs): every gradient
     against autograd through the fp64 restatement of GATConvNodes.message/aggregate."""
     monkeypatch.setattr(ops, "_F16X3_EDGE", f16)
+    _edge_backward_case(n_cry, k, heads, lo, hi, 128)
+
+
+@pytest.mark.parametrize("n_cry,k,heads,lo,hi,f", [(40, 12, 8, 2, 20, 256), (3, 24, 8, 100, 120, 256),
+                                                   (30, 12, 3, 2, 20, 256), (30, 12, 5, 2, 20, 128)])
+def test_edge_attention_fused_wide(n_cry, k, heads, lo, hi, f):
+    """The generalised f16 path: F = 256 as two virtual heads per head and a hidden width that is not a multiple of 64
+    (F = 256 -> Hd = int(640 / 1.5) = 426, zero-padded to 448) — BASELINE.json configs[3] (hidden 256, 8 heads) —
+    forward and every gradient against the fp64 restatement; the launch counter proves the fused kernels ran."""
+    before = _lib.launch_count()
+    _edge_backward_case(n_cry, k, heads, lo, hi, f, kink_tolerant_table=True)
+    assert _lib.launch_count() - before >= 10
+
+
+def _edge_backward_case(n_cry, k, heads, lo, hi, f, kink_tolerant_table=False):
     from cgat_b200.CGAT import MultiHeadNetwork
     from tests._cases import assert_grad_close
-    f, fe = 128, 128
+    fe = 128
     sb = synthetic.make_batch(n_cry, k, seed=100 + n_cry, atoms_lo=lo, atoms_hi=hi)
     gidx = sb.graph
     n = gidx.num_nodes
@@ -275,7 +290,14 @@ def test_edge_attention_fused_backward_all_grads(n_cry, k, heads, lo, hi, f16, m
     floor = (gu_tab.cpu().double() - tabd.grad).abs().max().item()
     err = (tabc.grad.cpu().double() - tabd.grad).abs().max().item()
     print(f"d_table: fused err {err:.3e}, library-fp32 err {floor:.3e}, ref max {tabd.grad.abs().max().item():.3e}")
-    assert err <= max(4 * floor, 1e-4 + 1e-3 * tabd.grad.abs().max().item() * 0.1), (err, floor)
+    if kink_tolerant_table:
+        # at 8 heads x 426 hidden units a LeakyReLU pre-activation within fp32 rounding of 0 is likely in ONE of the two
+        # evaluation orders (P[dst] + P[src] + T[rank] here, one GEMM over the concatenated input in the library):
+        # scripts/edge_wide_diag.py shows the fused and library errors identical to three digits when neither flips,
+        # and a single hidden unit's row off when one does — so the table gradient is held to the kink-aware criterion
+        assert_grad_close(tabc.grad, tabd.grad, "d_table")
+    else:
+        assert err <= max(4 * floor, 1e-4 + 1e-3 * tabd.grad.abs().max().item() * 0.1), (err, floor)
     for pre, mod in (("A.", mh_a), ("M.", mh_m)):
         for kk, p in mod.named_parameters():
             ref_g = sd[pre + kk].grad
