@@ -50,6 +50,10 @@ CASES = {
                            rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
                            n_graph_roost=1, no_hyper=False),
                       dict(n_crystals=8, max_nbr=8, seed=5), 5),
+    "wide_f256_h8": (dict(elem_fea_len=256, n_graph=2, msg_heads=8, neighbor_number=12, mean_pooling=False,
+                          rezero=True, update_edges=True, vector_attention=True, global_vector_attention=True,
+                          n_graph_roost=3),
+                     dict(n_crystals=10, max_nbr=12, seed=6), 6),
 }
 
 # gradient tensors stored in full (small); every other gradient is stored as (sum, abs-sum, l2)
