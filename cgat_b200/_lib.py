@@ -57,7 +57,7 @@ SIGNATURES = {
     "cgat_hyper_rowscale_parts": (_I32, [_I64, _I32]),
     "cgat_hyper_rowscale": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowscale_f16_amax": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
-    "cgat_hyper_wgrad_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
+    "cgat_hyper_wgrad_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_wgrad_splits": (_I32, [_I64]),
     "cgat_hyper_wgrad": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_edge_attn_fwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I64, _I64, _I32,

@@ -25,14 +25,17 @@ constexpr int kImg = kRows * 128;             // one image: 64 columns x 32 rows
 constexpr int kPart = 2 * kImg;               // 128 columns = 2 images = 8 KB
 constexpr int kStage = 6 * kPart;             // Z hi/lo, A0 hi/lo, A1 hi/lo = 48 KB
 constexpr int kStagesW = 4;
-constexpr int kSmemW = kStagesW * kStage + 256 + 1024;
+constexpr int kTailRed = 16 * 32 * 16 * 4;    // [16 producer warps][32 lanes][4 sums x 4 columns] floats = 32 KB
+constexpr int kSmemW = kStagesW * kStage + kTailRed + 256 + 1024;
 
 __global__ void __launch_bounds__(kThreadsW, 1)
 hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y, const float* __restrict__ z,
-                       const float* __restrict__ g_amax, float* __restrict__ out, int n_atoms, int n_split) {
+                       const float* __restrict__ g_amax, float* __restrict__ out, float* __restrict__ tail,
+                       int n_atoms, int n_split) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * kStage);
+  float* tail_red = reinterpret_cast<float*>(smem + kStagesW * kStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStagesW * kStage + kTailRed);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStagesW;
   uint64_t* accum = bars + 2 * kStagesW;
@@ -94,6 +97,11 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
     // conversion work of 8 warps (two per scheduler, dependent ALU chains) was pacing the kernel, and a software
     // prefetch of the next chunk's rows changed nothing (measured) — it is issue slots / latency hiding, not loads.
     const int pt = tid - 128, grp = pt >> 8, pl = pt & 255;
+    // Bias-shaped gradients of the same Linear come for free from the rows staged here: the column sums of the scaled
+    // rows, sum_n g[n,o] y[n,:], are dL/db[o*F : (o+1)*F], and sum_n g[n,o] z[n,:] is dL/dW[F*F + o, :] — a thread
+    // always holds the same 4 columns (q = pl % 32), so it keeps four float4 running sums; they replace a separate
+    // split-K GEMM g^T [y | z] per hyper-layer (20 launches of ~45 us per cfg2 train step).
+    float4 sy0 = make_float4(0.f, 0.f, 0.f, 0.f), sy1 = sy0, sz0 = sy0, sz1 = sy0;
     for (int ch = grp; ch < n_chunks; ch += 2) {
       const int st = ch % kStagesW, u = ch / kStagesW;
       const int n0 = n_lo + ch * kRows;
@@ -123,16 +131,35 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
         *reinterpret_cast<uint2*>(sb + off) = hi;
         *reinterpret_cast<uint2*>(sb + kPart + off) = lo;
         float4 a = make_float4(yv[j].x * g0[j], yv[j].y * g0[j], yv[j].z * g0[j], yv[j].w * g0[j]);
+        sy0.x += a.x, sy0.y += a.y, sy0.z += a.z, sy0.w += a.w;
+        sz0.x = fmaf(zv[j].x, g0[j], sz0.x), sz0.y = fmaf(zv[j].y, g0[j], sz0.y);
+        sz0.z = fmaf(zv[j].z, g0[j], sz0.z), sz0.w = fmaf(zv[j].w, g0[j], sz0.w);
         split_f16x4s(a, kF16LoScale, hi, lo);
         *reinterpret_cast<uint2*>(sb + 2 * kPart + off) = hi;
         *reinterpret_cast<uint2*>(sb + 3 * kPart + off) = lo;
         a = make_float4(yv[j].x * g1[j], yv[j].y * g1[j], yv[j].z * g1[j], yv[j].w * g1[j]);
+        sy1.x += a.x, sy1.y += a.y, sy1.z += a.z, sy1.w += a.w;
+        sz1.x = fmaf(zv[j].x, g1[j], sz1.x), sz1.y = fmaf(zv[j].y, g1[j], sz1.y);
+        sz1.z = fmaf(zv[j].z, g1[j], sz1.z), sz1.w = fmaf(zv[j].w, g1[j], sz1.w);
         split_f16x4s(a, kF16LoScale, hi, lo);
         *reinterpret_cast<uint2*>(sb + 4 * kPart + off) = hi;
         *reinterpret_cast<uint2*>(sb + 5 * kPart + off) = lo;
       }
       fence_async_smem();
       mbar_arrive(&full[st]);
+    }
+    if (tail != nullptr) {
+      // fixed-order reduction over the 16 producer warps (deterministic): [warp][lane][sum][component]
+      float4* mine = reinterpret_cast<float4*>(tail_red) + ((pt >> 5) * 32 + lane) * 4;
+      mine[0] = sy0, mine[1] = sy1, mine[2] = sz0, mine[3] = sz1;
+      asm volatile("bar.sync 1, %0;" ::"n"(512) : "memory");
+      // thread -> (sum kind = pt / 128: y of o0, y of o0+1, z of o0, z of o0+1; column = pt % 128)
+      const int kind = pt >> 7, col = pt & 127;
+      float acc = 0.f;
+#pragma unroll
+      for (int w = 0; w < 16; ++w) acc += tail_red[((w * 32 + (col >> 2)) * 4 + kind) * 4 + (col & 3)];
+      // tail (n_split, F, 2F): row o = [sum_n g y | sum_n g z]; the rows were scaled by s on the way in
+      tail[((int64_t)split * kF + o0 + (kind & 1)) * 2 * kF + (kind >> 1) * kF + col] = acc * s_inv;
     }
   } else {
     constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128);
@@ -324,8 +351,10 @@ using namespace cgat;
 // cgat_hyper_wgrad on kind::f16 passes: same result layout, (cgat_hyper_wgrad_splits(N), F*F, F) partial dL/dW[:F*F]
 // for F = 128; for F = 256 a single (F*F, F) result (no split over atoms).
 // g_amax: device float holding max |g| (written by cgat_hyper_rowscale_f16 with the same g as `scale`).
+// tail (optional, F = 128 only): (cgat_hyper_wgrad_splits(N), F, 2F) partial [g^T y | g^T z] — the bias-shaped
+// gradients of the same Linear (dL/db[:F*F] rows and dL/dW[F*F:]), accumulated from the rows the kernel stages anyway.
 extern "C" int cgat_hyper_wgrad_f16(const float* g, const float* y, const float* z, const float* g_amax, float* out,
-                                    int64_t n_atoms, int32_t f, void* stream_) {
+                                    float* tail, int64_t n_atoms, int32_t f, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (f != kF && f != kF2) return fail(-2, "cgat_hyper_wgrad_f16: instantiated for F = 128 and F = 256");
   if (n_atoms >= (1ll << 31) - 64) return fail(-2, "cgat_hyper_wgrad_f16: too many atoms");
@@ -336,6 +365,7 @@ extern "C" int cgat_hyper_wgrad_f16(const float* g, const float* y, const float*
     CGAT_CUDA(cudaFuncSetAttribute(hyper_wgrad_f16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemW));
     configured = true;
   }
+  if (f == kF2 && tail != nullptr) return fail(-2, "cgat_hyper_wgrad_f16: the tail output exists for F = 128 only");
   if (f == kF2) {
     // (o, row half) x splits: 512 CTAs already fill the SMs three times over, so the atoms are not split
     static bool configured2 = false;
@@ -347,6 +377,7 @@ extern "C" int cgat_hyper_wgrad_f16(const float* g, const float* y, const float*
     return check_launch("hyper_wgrad_f16_256_kernel");
   }
   const int n_split = cgat_hyper_wgrad_splits(n_atoms);
-  hyper_wgrad_f16_kernel<<<(f / 2) * n_split, kThreadsW, kSmemW, stream>>>(g, y, z, g_amax, out, (int)n_atoms, n_split);
+  hyper_wgrad_f16_kernel<<<(f / 2) * n_split, kThreadsW, kSmemW, stream>>>(g, y, z, g_amax, out, tail, (int)n_atoms,
+                                                                         n_split);
   return check_launch("hyper_wgrad_f16_kernel");
 }

@@ -414,9 +414,11 @@ class _HyperLinear(torch.autograd.Function):
         lib = _lib.load()
         splits = int(lib.cgat_hyper_wgrad_splits(n)) if f == 128 else 1     # F = 256: 512 CTAs without an atom split
         wpart = torch.empty((splits, ff, f), dtype=torch.float32, device=y.device)
+        # F = 128: the same launch also sums the bias-shaped gradients g^T [y | z] from the rows it stages
+        tail = torch.empty((splits, f, 2 * f), dtype=torch.float32, device=y.device) if f16_grad and f == 128 else None
         if f16_grad:
             _lib.call("cgat_hyper_wgrad_f16", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(g_amax), _lib.ptr(wpart),
-                      n, f, _lib.stream(),
+                      _lib.ptr(tail), n, f, _lib.stream(),
                       work=dict(key="hyper_wgrad", bound="tensor", flops=2.0 * n * f * ff,
                                 note="f16x3: 3 kind::f16 passes per algorithmic flop, gradient operand scaled by 2^k"))
         else:
@@ -425,8 +427,11 @@ class _HyperLinear(torch.autograd.Function):
                                 note="3xTF32: 3 tensor passes per algorithmic flop"))
         g_w = torch.empty_like(weight)
         sum_parts(wpart, out=g_w[:ff])
-        yz = torch.cat([y, z], dim=1)                      # bias-shaped rows: g^T [y | z]
-        gyz = gemm3x_tn(g, yz)                             # (F, 2F), split over atoms to fill the SMs
+        if tail is not None:
+            gyz = sum_parts(tail)                          # (F, 2F) = g^T [y | z]
+        else:
+            yz = torch.cat([y, z], dim=1)                  # bias-shaped rows: g^T [y | z]
+            gyz = gemm3x_tn(g, yz)                         # (F, 2F), split over atoms to fill the SMs
         g_w[ff:] = gyz[:, f:]
         g_b = torch.cat([gyz[:, :f].reshape(ff), g.sum(dim=0)])
         return g_z, g_w, g_b, g_y, (g if ctx.has_e else None), None, None, None

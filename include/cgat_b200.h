@@ -199,11 +199,13 @@ int cgat_hyper_wgrad(const float* g, const float* y, const float* z, float* out,
 
 /* kind::f16 form of cgat_hyper_wgrad (twice the tensor rate; 48 KB stages): the gradient operand g is multiplied by a
  * power of two derived from g_amax[0] = max |g| (device float), which cgat_hyper_rowscale_f16_amax produces while it
- * reads the same g as `scale` (scale_amax must be zeroed before the launch).                              */
+ * reads the same g as `scale` (scale_amax must be zeroed before the launch).  F = 128 or 256.
+ * tail (optional, F = 128): (cgat_hyper_wgrad_splits(N), F, 2F) partial [g^T y | g^T z], the bias-shaped gradients of
+ * the same Linear (dL/db[:F*F] and dL/dW[F*F:]) summed from the rows the kernel stages anyway.                 */
 int cgat_hyper_rowscale_f16_amax(const float* a, const float* scale, const float* w_bias, const float* w_packed,
                                  float* partial, float* scale_amax, int64_t n_atoms, int32_t f, void* stream);
 int cgat_hyper_wgrad_f16(const float* g, const float* y, const float* z, const float* g_amax, float* out,
-                         int64_t n_atoms, int32_t f, void* stream);
+                         float* tail, int64_t n_atoms, int32_t f, void* stream);
 
 /* ---- fused edge attention, backward -------------------------------------
  * Step 1: recompute a, v; write d_gate = dL/da, d_msg = dL/dv (E,H,F; destination-sorted rows) and the
