@@ -193,7 +193,7 @@ class CGAtNet(nn.Module):
         n_cry = getattr(batch, "num_graphs", None)
         if n_cry is None:
             n_cry = int(batch.batch[-1]) + 1
-        plan = build_edge_plan(batch.edge_index, batch.edge_attr, n_atoms)
+        plan = build_edge_plan(batch.edge_index, batch.edge_attr, n_atoms, self.nbr_embedding.num_embeddings)
         cry_plan = build_segment_plan(batch.batch, n_cry)
 
         x = self.embedding(batch.x)                                # reference :570

@@ -19,7 +19,7 @@ _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
 
-ABI_VERSION = 4  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
+ABI_VERSION = 5  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
 
 # name -> (restype, argtypes); must list every symbol declared in include/cgat_b200.h
 SIGNATURES = {
@@ -27,7 +27,8 @@ SIGNATURES = {
     "cgat_last_error": (ctypes.c_char_p, []),
     "cgat_launch_count": (_I64, []),
     "cgat_csr_workspace_bytes": (_SZ, [_I64, _I64]),
-    "cgat_csr_build": (ctypes.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "cgat_csr_build": (ctypes.c_int, [_P, _P, _I64, _I64, _P, _P, _P, _P, _P, _I32, _P, _SZ, _P]),
+    "cgat_status_flags": (ctypes.c_int, [_P, _I32]),
     "cgat_segment_ptr": (ctypes.c_int, [_P, _I64, _I64, _P, _P, _P]),
     "cgat_seg_softmax_fwd": (ctypes.c_int, [_P, _P, _P, _P, _I64, _I32, _I32, _I32, _F32, _P, _P, _P, _P]),
     "cgat_seg_softmax_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _I32, _F32,
@@ -167,6 +168,31 @@ def profile_end():
         r["bytes"] += float(work.get("bytes", 0))
         r["flops"] += float(work.get("flops", 0))
     return rows
+
+
+STATUS_BITS = {1: "an edge destination (edge_index[1]) is outside [0, num_nodes): the edge was dropped",
+               2: "an edge source (edge_index[0]) is outside [0, num_nodes): clamped to 0",
+               4: "a shell rank (edge_attr) is outside the rank-embedding table: clamped to 0",
+               8: "a non-finite aggregate left the fused edge attention (fp16 operand overflow of a diverged network, "
+                  "or NaN / Inf inputs); CGAT_B200_F16X3_EDGE=0 selects the tf32 kernels"}
+
+
+def status_flags(reset=True):
+    """Sticky validation flags raised by kernels since the last reset (include/cgat_b200.h: cgat_status_flags).
+    Synchronises the device."""
+    out = ctypes.c_uint32(0)
+    rc = load().cgat_status_flags(ctypes.byref(out), int(reset))
+    if rc != 0:
+        raise CgatLibraryError(f"cgat_status_flags failed: {load().cgat_last_error().decode()}")
+    return int(out.value)
+
+
+def check_status(reset=True):
+    """Raise if any kernel flagged invalid input / a non-finite result since the last call (the reference raises an
+    IndexError from nn.Embedding / index_select at the same inputs).  Synchronises: call it after a step, not inside."""
+    v = status_flags(reset)
+    if v:
+        raise CgatLibraryError("cgat_b200: " + "; ".join(msg for bit, msg in STATUS_BITS.items() if v & bit))
 
 
 def launch_count():

@@ -38,6 +38,16 @@ inline int check_launch(const char* name) {
 
 constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
 
+// Library-wide device status word (sticky flags raised by kernels, read by cgat_status_flags — the one entry point
+// that synchronises).  Kernels get the pointer as an argument: device symbols do not link across translation units.
+enum StatusBits : unsigned int {
+  kStatusBadDestination = 1u,   // cgat_csr_build: edge_index[1] outside [0, n_nodes)  (the edge is dropped)
+  kStatusBadSource = 2u,        // cgat_csr_build: edge_index[0] outside [0, n_nodes)  (clamped to 0)
+  kStatusBadRank = 4u,          // cgat_csr_build: edge_attr outside [0, n_ranks)       (clamped to 0)
+  kStatusNonFinite = 8u,        // cgat_edge_attn_fwd*: a non-finite aggregate (fp16 operand overflow, or NaN/Inf input)
+};
+unsigned int* status_word();   // device address of the word (csr_build.cu)
+
 __host__ __device__ inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // hyper-linear kernels: output channels per work item — smaller chunks when there are few atom tiles, so that all

@@ -13,6 +13,14 @@ namespace cgat {
 thread_local char g_err[512] = "";
 long long g_launches = 0;
 
+__device__ unsigned int g_status_word = 0;
+
+unsigned int* status_word() {
+  static unsigned int* p = nullptr;
+  if (p == nullptr) cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_status_word);
+  return p;
+}
+
 namespace {
 
 constexpr int kScanThreads = 1024;
@@ -20,12 +28,14 @@ constexpr int kScanItems = 4;  // items per thread
 constexpr int kScanTile = kScanThreads * kScanItems;
 
 __global__ void histogram_kernel(const int64_t* __restrict__ dst, int64_t n_edges, int64_t n_nodes,
-                                 int32_t* __restrict__ counts, int32_t* __restrict__ bad) {
+                                 int32_t* __restrict__ counts, int32_t* __restrict__ bad,
+                                 unsigned int* __restrict__ status) {
   int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n_edges) return;
   int64_t d = dst[e];
   if (d < 0 || d >= n_nodes) {
     atomicAdd(bad, 1);
+    atomicOr(status, (unsigned int)kStatusBadDestination);
     return;
   }
   atomicAdd(&counts[d], 1);  // integer atomics: result independent of order
@@ -122,7 +132,8 @@ __global__ void fill_kernel(const int64_t* __restrict__ dst, int64_t n_edges, in
 __global__ void order_kernel(const int64_t* __restrict__ src, const int64_t* __restrict__ attr,
                              const int32_t* __restrict__ rowptr, const int32_t* __restrict__ slots,
                              int64_t n_nodes, int32_t* __restrict__ perm, int32_t* __restrict__ src_sorted,
-                             int32_t* __restrict__ dst_sorted, int32_t* __restrict__ rank_sorted) {
+                             int32_t* __restrict__ dst_sorted, int32_t* __restrict__ rank_sorted, int64_t n_ranks,
+                             unsigned int* __restrict__ status) {
   int64_t d = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   int lane = threadIdx.x & 31;
   if (d >= n_nodes) return;
@@ -133,9 +144,14 @@ __global__ void order_kernel(const int64_t* __restrict__ src, const int64_t* __r
     for (int32_t q = b; q < e; ++q) r += (slots[q] < id);
     int32_t o = b + r;
     perm[o] = id;
-    src_sorted[o] = (int32_t)src[id];
+    // what nn.Embedding / index_select would refuse in the reference becomes a sticky status flag here (no sync on
+    // the hot path) and the index is clamped, so no kernel downstream gathers out of bounds
+    int64_t sv = src[id], rv = attr[id];
+    if (sv < 0 || sv >= n_nodes) atomicOr(status, (unsigned int)kStatusBadSource), sv = 0;
+    if (rv < 0 || rv >= n_ranks) atomicOr(status, (unsigned int)kStatusBadRank), rv = 0;
+    src_sorted[o] = (int32_t)sv;
     dst_sorted[o] = (int32_t)d;
-    rank_sorted[o] = (int32_t)attr[id];
+    rank_sorted[o] = (int32_t)rv;
   }
 }
 
@@ -168,9 +184,10 @@ extern "C" size_t cgat_csr_workspace_bytes(int64_t n_edges, int64_t n_nodes) {
 
 extern "C" int cgat_csr_build(const int64_t* edge_index, const int64_t* edge_attr, int64_t n_edges,
                               int64_t n_nodes, int32_t* perm, int32_t* rowptr, int32_t* src_sorted,
-                              int32_t* dst_sorted, int32_t* rank_sorted, void* workspace,
+                              int32_t* dst_sorted, int32_t* rank_sorted, int32_t n_ranks, void* workspace,
                               size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
+  if (n_ranks <= 0 || n_ranks > 32) n_ranks = 32;   // the edge kernels index per-rank tables of at most 32 rows
   if (n_edges < 0 || n_nodes < 0 || n_edges >= (1ll << 31) || n_nodes >= (1ll << 31) - 1)
     return fail(-2, "cgat_csr_build: sizes out of int32 range");
   if (workspace_bytes < cgat_csr_workspace_bytes(n_edges, n_nodes))
@@ -187,7 +204,8 @@ extern "C" int cgat_csr_build(const int64_t* edge_index, const int64_t* edge_att
 
   CGAT_CUDA(cudaMemsetAsync(ws, 0, sizeof(int32_t) * (size_t)(4 + 2 * (n_nodes + 1)), stream));
   if (n_edges > 0) {
-    histogram_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(dst, n_edges, n_nodes, counts, bad);
+    histogram_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(dst, n_edges, n_nodes, counts, bad,
+                                                                           status_word());
     if (int e = check_launch("histogram_kernel")) return e;
   }
   // exclusive scan of counts[0..N] (counts[N] = 0) -> rowptr[0..N]; rowptr[N] = E
@@ -201,8 +219,23 @@ extern "C" int cgat_csr_build(const int64_t* edge_index, const int64_t* edge_att
     fill_kernel<<<(unsigned)ceil_div(n_edges, 256), 256, 0, stream>>>(dst, n_edges, n_nodes, rowptr, cursor, slots);
     if (int e = check_launch("fill_kernel")) return e;
     order_kernel<<<(unsigned)ceil_div(n_nodes * 32, 256), 256, 0, stream>>>(src, edge_attr, rowptr, slots, n_nodes,
-                                                                           perm, src_sorted, dst_sorted, rank_sorted);
+                                                                           perm, src_sorted, dst_sorted, rank_sorted,
+                                                                           n_ranks, status_word());
     if (int e = check_launch("order_kernel")) return e;
+  }
+  return 0;
+}
+
+// Sticky validation flags raised by kernels since the last reset (bit 0: destination, bit 1: source, bit 2: shell rank
+// out of range in cgat_csr_build; bit 3: non-finite aggregate in cgat_edge_attn_fwd*).  SYNCHRONISES the device: call
+// it where a sync is acceptable (after a step, in tests), not on the hot path.
+extern "C" int cgat_status_flags(uint32_t* flags_out, int32_t reset) {
+  unsigned int v = 0;
+  CGAT_CUDA(cudaMemcpyFromSymbol(&v, g_status_word, sizeof(v)));
+  if (flags_out) *flags_out = v;
+  if (reset && v) {
+    const unsigned int zero = 0;
+    CGAT_CUDA(cudaMemcpyToSymbol(g_status_word, &zero, sizeof(zero)));
   }
   return 0;
 }

@@ -74,6 +74,7 @@ struct EdgeArgs {
   float eps;
   int n_stages;         // operand ring depth: 3, or 2 with L1 prefetch of the gathered rows (f16 path)
   int vh;               // 128-channel blocks per real head (F / 128): F = 256 runs every real head as two virtual heads
+  unsigned int* status; // library status word: kStatusNonFinite is raised when an aggregate is not finite
 };
 
 __device__ __forceinline__ int lower_bound_i32(const int32_t* a, int n, int64_t key) {
@@ -220,7 +221,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             if (d0 != d) {
               if (d >= 0) {
                 const int64_t o = (int64_t)d * hf + hc;
-                g.out[o] = acc / (den + g.eps);
+                const float r = acc / (den + g.eps);
+                if (!(fabsf(r) <= 3.0e38f)) atomicOr(g.status, (unsigned int)kStatusNonFinite);
+                g.out[o] = r;
                 if (g.smax) g.smax[o] = m, g.sden[o] = den;
               }
               m = -INFINITY, den = 0.f, acc = 0.f;
@@ -239,7 +242,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               const int t = cc * 16 + j;
               if ((sflags >> j) & 1u) {  // edge t opens a new segment: flush the finished one (never at t = 0)
                 const int po = mt[3 * kET + t - 1] + hc;
-                g.out[po] = acc * fast_rcp(den + g.eps);
+                const float r = acc * fast_rcp(den + g.eps);
+                if (!(fabsf(r) <= 3.0e38f)) atomicOr(g.status, (unsigned int)kStatusNonFinite);
+                g.out[po] = r;
                 if (g.smax != nullptr) g.smax[po] = m, g.sden[po] = den;
                 m = -INFINITY, den = 0.f, acc = 0.f;
               }
@@ -259,7 +264,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           mbar_arrive(&tmem_empty[hb]);
           if (last_tile) {
             const int64_t o = (int64_t)d * hf + hc;
-            g.out[o] = acc / (den + g.eps);
+            const float r = acc / (den + g.eps);
+            if (!(fabsf(r) <= 3.0e38f)) atomicOr(g.status, (unsigned int)kStatusNonFinite);
+            g.out[o] = r;
             if (g.smax) g.smax[o] = m, g.sden[o] = den;
           } else {
             cs[c] = m, cs[kEF + c] = den, cs[2 * kEF + c] = acc;
@@ -614,7 +621,7 @@ int edge_fwd_impl(const float* P, const float* T, const int32_t* rowptr, const i
   if (n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads * (f / kEF), hd,
-             eps, 0, f / kEF};
+             eps, 0, f / kEF, status_word()};
   return launch_edge<0, kF16>(a, stream);
 }
 
@@ -633,7 +640,7 @@ int edge_bwd_prep_impl(const float* P, const float* T, const int32_t* rowptr, co
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
              const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs, bias_sums,
              reinterpret_cast<unsigned int*>(dz_amax), (int)n_atoms, (int)n_edges, heads * (f / kEF), hd, eps, 0,
-             f / kEF};
+             f / kEF, status_word()};
   return launch_edge<1, kF16>(a, stream);
 }
 }  // namespace

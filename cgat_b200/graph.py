@@ -55,7 +55,7 @@ class SegmentPlan:
     index: torch.Tensor     # (n_rows,) int32
 
 
-def _csr(edge_index, edge_attr, n_nodes):
+def _csr(edge_index, edge_attr, n_nodes, n_ranks=0):
     dev = edge_index.device
     E = edge_index.shape[1]
     lib = _lib.load()
@@ -65,18 +65,20 @@ def _csr(edge_index, edge_attr, n_nodes):
     ws_bytes = int(lib.cgat_csr_workspace_bytes(E, n_nodes))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     _lib.call("cgat_csr_build", _lib.ptr(edge_index), _lib.ptr(edge_attr), E, n_nodes, _lib.ptr(perm),
-              _lib.ptr(rowptr), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(rank), _lib.ptr(ws), ws_bytes,
+              _lib.ptr(rowptr), _lib.ptr(src), _lib.ptr(dst), _lib.ptr(rank), int(n_ranks), _lib.ptr(ws), ws_bytes,
               _lib.stream())
     return perm, rowptr, src, dst, rank
 
 
-def build_edge_plan(edge_index: torch.Tensor, edge_attr: torch.Tensor, n_nodes: int) -> EdgePlan:
-    """edge_index (2,E) int64 [source; destination] (reference CGAT/data.py:140), edge_attr (E,) int64."""
+def build_edge_plan(edge_index: torch.Tensor, edge_attr: torch.Tensor, n_nodes: int, n_ranks: int = 0) -> EdgePlan:
+    """edge_index (2,E) int64 [source; destination] (reference CGAT/data.py:140), edge_attr (E,) int64.
+    n_ranks: rows of the shell-rank embedding table (0: unknown, the kernels' limit of 32 is used); out-of-range node ids
+    / ranks raise a sticky device flag (_lib.check_status) instead of gathering out of bounds."""
     if edge_index.dtype != torch.int64 or edge_attr.dtype != torch.int64:
         raise TypeError("edge_index / edge_attr must be int64 (the reference's layout)")
     edge_index = edge_index.contiguous()
     edge_attr = edge_attr.contiguous()
-    perm, rowptr, src, dst, rank = _csr(edge_index, edge_attr, n_nodes)
+    perm, rowptr, src, dst, rank = _csr(edge_index, edge_attr, n_nodes, n_ranks)
     return EdgePlan(n_nodes, edge_index.shape[1], perm, rowptr, src, dst, rank, edge_index, edge_attr)
 
 

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CGAT_B200_ABI_VERSION 4 /* 2: bwd_prep gained bias_sums; f16 entry points. 3: train-step glue. 4: bwd_prep gained dz_amax */
+#define CGAT_B200_ABI_VERSION 5 /* 2: bwd_prep bias_sums; f16 entry points. 3: train-step glue. 4: dz_amax. 5: n_ranks, status flags */
 
 int cgat_abi_version(void);
 const char* cgat_last_error(void);
@@ -41,7 +41,14 @@ int64_t cgat_launch_count(void);
 size_t cgat_csr_workspace_bytes(int64_t n_edges, int64_t n_nodes);
 int cgat_csr_build(const int64_t* edge_index, const int64_t* edge_attr, int64_t n_edges, int64_t n_nodes,
                    int32_t* perm, int32_t* rowptr, int32_t* src_sorted, int32_t* dst_sorted,
-                   int32_t* rank_sorted, void* workspace, size_t workspace_bytes, void* stream);
+                   int32_t* rank_sorted, int32_t n_ranks, void* workspace, size_t workspace_bytes, void* stream);
+/* Input validation without a sync on the hot path: what nn.Embedding / index_select refuse in the reference (a node id
+ * outside [0, n_nodes), a shell rank outside [0, n_ranks); n_ranks <= 0 means 32, the kernels' table limit) raises a
+ * STICKY flag in device memory and the index is clamped (a bad destination drops the edge), so nothing downstream
+ * gathers out of bounds.  cgat_status_flags reads (and optionally clears) the flags — it synchronises the device:
+ * bit 0 destination, bit 1 source, bit 2 shell rank out of range; bit 3 a non-finite aggregate left
+ * cgat_edge_attn_fwd* (fp16 operand overflow of a diverged network, or NaN / Inf inputs).                       */
+int cgat_status_flags(uint32_t* flags_out, int32_t reset);
 
 /* ptr (n_seg+1) of a SORTED int64 segment index vector: crystal_ptr from batch.batch
  * (CGAT/CGAT.py:567), Roost row pointers from self_fea_idx / crystal_elem_idx

@@ -8,7 +8,7 @@ from cgat_b200 import graph, ops
 from oracle import cgat_oracle as O
 
 
-def build_edge_plan(edge_index, edge_attr, n_nodes):
+def build_edge_plan(edge_index, edge_attr, n_nodes, n_ranks=0):
     perm, rowptr = O.csr_by_destination(edge_index, n_nodes)
     i32 = lambda t: t.to(torch.int32)
     return graph.EdgePlan(n_nodes, edge_index.shape[1], i32(perm), i32(rowptr), i32(edge_index[0][perm]),

@@ -459,3 +459,30 @@ def test_device_collation_bit_exact(n_store, n_sel, k, seed):
     assert list(dev.n_atoms) == list(host.n_atoms)
     # and the model sees the same thing
     assert batching.signature(dev) == batching.signature(host)
+
+
+def test_status_flags_for_out_of_range_input():
+    """What the reference's nn.Embedding / index_select refuse (a shell rank beyond the table, a node id beyond the
+    batch) raises a sticky device flag instead of gathering out of bounds; clean input leaves the flags clear."""
+    _lib.status_flags(reset=True)
+    sb = synthetic.make_batch(5, 12, seed=0)
+    g = sb.graph
+    n = g.num_nodes
+    plan = graph.build_edge_plan(g.edge_index.to(DEV), g.edge_attr.to(DEV), n, 13)
+    assert _lib.status_flags(reset=True) == 0
+    assert int(plan.rank.max()) <= 12
+    bad_attr = g.edge_attr.clone()
+    bad_attr[3] = 13                                        # one past the (K+1)-row table
+    plan = graph.build_edge_plan(g.edge_index.to(DEV), bad_attr.to(DEV), n, 13)
+    assert _lib.status_flags(reset=False) & 4
+    assert int(plan.rank.max()) <= 12                       # clamped: nothing downstream reads out of bounds
+    with pytest.raises(_lib.CgatLibraryError, match="shell rank"):
+        _lib.check_status()
+    assert _lib.status_flags() == 0                         # check_status cleared them
+    bad_ei = g.edge_index.clone()
+    bad_ei[0, 7] = n + 5
+    bad_ei[1, 9] = -1
+    plan = graph.build_edge_plan(bad_ei.to(DEV), g.edge_attr.to(DEV), n, 13)
+    flags = _lib.status_flags(reset=True)
+    assert flags & 1 and flags & 2 and not flags & 4
+    assert int(plan.src.max()) < n and int(plan.rowptr[-1]) == g.edge_index.shape[1] - 1   # the bad edge was dropped
