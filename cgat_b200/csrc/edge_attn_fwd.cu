@@ -72,7 +72,6 @@ struct EdgeArgs {
   unsigned int* dz_amax;  // backward-prep (optional): max |d_gate|, |d_msg| as float bits (range of the f16 wgrad / dgrad)
   int n_atoms, n_edges, heads, hd;   // heads = VIRTUAL heads = real heads * vh
   float eps;
-  int n_stages;         // operand ring depth: 3, or 2 with L1 prefetch of the gathered rows (f16 path)
   int vh;               // 128-channel blocks per real head (F / 128): F = 256 runs every real head as two virtual heads
   unsigned int* status; // library status word: kStatusNonFinite is raised when an aggregate is not finite
 };
@@ -129,8 +128,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* stages = smem;
-  const uint32_t nst = (uint32_t)g.n_stages;
-  int32_t* meta = reinterpret_cast<int32_t*>(smem + nst * kEStageBytes);                // [4][dst|src|rank|off|flags|valid]
+  int32_t* meta = reinterpret_cast<int32_t*>(smem + kEStages * kEStageBytes);                // [4][dst|src|rank|off|flags|valid]
   float* carry = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(meta) + kEMetaBytes);  // [H][4][128]
   uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(carry) + kECarryBytes);
   uint64_t* full = bars;                        // [3]
@@ -359,7 +357,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
         for (int net = 0; net < 2; ++net) {
           for (int kc = 0; kc < kcn; ++kc, ++cnt) {
             if (kEProducers > kEGroup && (cnt & 1u) != grp) continue;
-            const uint32_t s = nst == 2 ? (cnt & 1u) : cnt % kEStages, u = nst == 2 ? (cnt >> 1) : cnt / kEStages;
+            const uint32_t s = cnt % kEStages, u = cnt / kEStages;
             mbar_wait(&empty[s], (u + 1) & 1u);
             uint8_t* st = stages + s * kEStageBytes;
             if (pl == 0) {
@@ -472,32 +470,6 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             }
             fence_async_smem();
             mbar_arrive(&full[s]);
-            if (kF16 && nst == 2) {
-              // Two-stage ring: the shared memory given up (64 KB) becomes L1, and the rows this group gathers for
-              // its NEXT stage (two stages ahead in the pipeline) are requested into it now, fire-and-forget, so the
-              // LDG.256s of that stage find them there instead of waiting on L2 with a handful of loads in flight
-              // (ncu r01h: 35 % of the samples on the first use of a gathered value).
-              int kc2 = kc, net2 = net, h2 = h;
-#pragma unroll
-              for (int a = 0; a < 2; ++a)
-                if (++kc2 == kcn) {
-                  kc2 = 0;
-                  if (++net2 == 2) net2 = 0, ++h2;
-                }
-              if (h2 < H && (pl & 3) == 0) {  // one thread per 128-byte line: chunks 0-3 / 4-7 of a 256-byte row slice
-                const int colp = net2 * hhd + (h2 / vh) * hd + kc2 * kPackChunk16 + ((pl >> 2) & 1) * 32;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int r = (pl + kEGroup * j) >> 3;
-                  const int d = mt[r];
-                  if (d >= 0) {
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.P + (int64_t)d * ldp + colp));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.P + (int64_t)mt[kET + r] * ldp + 2 * hhd + colp));
-                    asm volatile("prefetch.global.L1 [%0];" ::"l"(g.T + (int64_t)mt[2 * kET + r] * ldt + colp));
-                  }
-                }
-              }
-            }
           }
         }
       }
@@ -514,7 +486,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
         for (int net = 0; net < 2; ++net) {
           const uint32_t d = tmem + hb * 256 + net * 128;
           for (int kc = 0; kc < kcn; ++kc, ++cnt) {
-            const uint32_t s = nst == 2 ? (cnt & 1u) : cnt % kEStages, u = nst == 2 ? (cnt >> 1) : cnt / kEStages;
+            const uint32_t s = cnt % kEStages, u = cnt / kEStages;
             mbar_wait(&full[s], u & 1u);
             tc_fence_after();
             if (lane == 0) {
@@ -571,28 +543,13 @@ int check_edge_args(int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t f, 
   return 0;
 }
 
-// CGAT_B200_EDGE_PREFETCH=1: two-stage operand ring + L1 prefetch of the next stage's gathered rows on the f16 path.
-// Parity-green but measured slightly SLOWER on B200 (cfg3: 2.61 vs 2.56 ms per launch), so it is opt-in: giving the
-// freed 64 KB to L1 and prefetching does not buy back what the third pipeline stage was hiding.
-bool edge_prefetch() {
-  static const bool on = [] {
-    const char* e = getenv("CGAT_B200_EDGE_PREFETCH");
-    return e && e[0] == '1';
-  }();
-  return on;
-}
-
 template <int kMode, bool kF16 = false>
 int launch_edge(EdgeArgs a, cudaStream_t stream) {
-  a.n_stages = (kF16 && edge_prefetch()) ? 2 : kEStages;
-  const int smem_bytes = kESmemBytes - (kEStages - a.n_stages) * kEStageBytes;
+  const int smem_bytes = kESmemBytes;
   static bool configured = false;
   if (!configured) {
     CGAT_CUDA(cudaFuncSetAttribute(edge_attn_kernel<kMode, kF16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    kESmemBytes));
-    if (a.n_stages == 2)  // leave the rest of the 256 KB to L1: that is where the prefetched rows wait
-      CGAT_CUDA(cudaFuncSetAttribute(edge_attn_kernel<kMode, kF16>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (smem_bytes + 1024) * 100 / (228 * 1024) + 1));
     configured = true;
   }
   const int64_t tiles = ceil_div(a.n_edges, kET);
@@ -621,7 +578,7 @@ int edge_fwd_impl(const float* P, const float* T, const int32_t* rowptr, const i
   if (n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, out, seg_max, seg_den,
              nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, (int)n_atoms, (int)n_edges, heads * (f / kEF), hd,
-             eps, 0, f / kEF, status_word()};
+             eps, f / kEF, status_word()};
   return launch_edge<0, kF16>(a, stream);
 }
 
@@ -639,7 +596,7 @@ int edge_bwd_prep_impl(const float* P, const float* T, const int32_t* rowptr, co
   if (n_atoms <= 0 || n_edges <= 0) return 0;
   EdgeArgs a{P, T, rowptr, src, dst, rank, w2a_packed, w2m_packed, b2a, b2m, const_cast<float*>(out),
              const_cast<float*>(seg_max), const_cast<float*>(seg_den), g_out, d_gate, d_msg, signs, bias_sums,
-             reinterpret_cast<unsigned int*>(dz_amax), (int)n_atoms, (int)n_edges, heads * (f / kEF), hd, eps, 0,
+             reinterpret_cast<unsigned int*>(dz_amax), (int)n_atoms, (int)n_edges, heads * (f / kEF), hd, eps,
              f / kEF, status_word()};
   return launch_edge<1, kF16>(a, stream);
 }

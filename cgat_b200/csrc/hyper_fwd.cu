@@ -26,14 +26,13 @@ namespace cgat {
 namespace {
 using namespace tc;
 
-// kTS: the z tile (A operand) lives in TENSOR memory (written by the stagers with tcgen05.st) and the MMAs run in
-// TS mode: shared memory then only feeds B (12 KB instead of 20 KB of operand reads per K step) and holds a 7-stage
-// weight ring; the price is a single accumulator buffer (TMEM: 256 accumulator + 256 operand columns).
-template <int F, bool kTS = false>
+// (A variant with the z tile in TENSOR memory — tcgen05.st by the stagers, TS-mode MMAs, 7-stage weight ring, single
+// accumulator buffer — was measured slower in round 1, 140 vs 112 us backward, and has been removed: DESIGN.md §3.)
+template <int F>
 struct HyperCfg {
   static constexpr int kKC = F / kPackChunk;                    // K chunks of 32 floats
-  static constexpr int kABytes = kTS ? 0 : kKC * (int)kPackStageBytes;  // z tile in shared memory, hi+lo per chunk
-  static constexpr int kStages = kTS ? 7 : 3;                   // + 32 KB weight stages = 224 KB either way
+  static constexpr int kABytes = kKC * (int)kPackStageBytes;    // z tile in shared memory, hi+lo per chunk
+  static constexpr int kStages = 3;                             // + 32 KB weight stages = 224 KB
   static constexpr int kBarBytes = 512;
   static constexpr int kSmemBytes = kABytes + kStages * (int)kPackStageBytes + 1024 + kBarBytes;
   static constexpr int kThreads = 416;
@@ -48,14 +47,13 @@ struct HyperCfg {
 //   with D_o[n,j] = sum_m z[n,m] Wblk_o[j,m].  Backward uses it twice: (z, W blocks) -> dL/dy_in and
 //   (y, transposed W blocks) -> dL/dz, i.e. both activation gradients of the hyper-linear layer without ever
 //   forming the (N, F*F) predicted-weight tensor or its gradient.
-template <int F, int kMode, bool kTS>
+template <int F, int kMode>
 __global__ void __launch_bounds__(HyperCfg<F>::kThreads, 1)
 hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y_in, const float* __restrict__ e_term,
                         const float* __restrict__ e_term2, const float* __restrict__ w_bias,
                         const float* __restrict__ w_packed, float* __restrict__ y_out, int n_atoms, int oc, int n_slots) {
-  using Cfg = HyperCfg<F, kTS>;
+  using Cfg = HyperCfg<F>;
   static_assert(F == 128, "row-in-registers epilogue is instantiated for F = 128");
-  constexpr uint32_t kAHiCol = 2 * F, kALoCol = 3 * F;  // kTS: operand columns behind the accumulator
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* a_smem = smem;                                   // [kKC][hi|lo][16 KB]
@@ -124,9 +122,9 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
       float accs[16];  // kMode 0: half dot products of this item's <= 16 outputs
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
         const int o = chunk * oc + oi;
-        const uint32_t b = kTS ? 0u : (ocount & 1u);
+        const uint32_t b = ocount & 1u;
         const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
-        mbar_wait(&tmem_full[b], (kTS ? ocount : (ocount >> 1)) & 1u);
+        mbar_wait(&tmem_full[b], (ocount >> 1) & 1u);
         tc_fence_after();
         float acc = 0.f;
         const uint32_t tb = tmem + lane_base + b * 2 * F + grp * HF;
@@ -199,33 +197,6 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
       const bool restage = tile != staged_tile;
       staged_tile = tile;
       if (restage) mbar_wait(a_free, (it + 1) & 1u);  // the previous tile's MMAs have finished reading the z tile
-      if (kTS) {
-        if (restage) {
-          // thread = atom row = TMEM lane: 32 columns of z at a time, split into tf32 hi/lo, written to the operand
-          // columns with tcgen05.st (stager warps 8-11 cover the lane quadrants 0-3)
-          tc_fence_after();
-          const int r = (warp & 3) * 32 + lane;
-          const int gr = tile * 128 + r;
-          const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-#pragma unroll 1
-          for (int kc = 0; kc < Cfg::kKC; ++kc) {
-            float hi[32], lo[32];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 v = gr < n_atoms ? __ldg(reinterpret_cast<const float4*>(z + (int64_t)gr * F + kc * 32) + j)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-              float4 h, l;
-              split_tf32(v, h, l);
-              hi[4 * j] = h.x, hi[4 * j + 1] = h.y, hi[4 * j + 2] = h.z, hi[4 * j + 3] = h.w;
-              lo[4 * j] = l.x, lo[4 * j + 1] = l.y, lo[4 * j + 2] = l.z, lo[4 * j + 3] = l.w;
-            }
-            tmem_st32(tmem + lane_base + kAHiCol + kc * 32, hi);
-            tmem_st32(tmem + lane_base + kALoCol + kc * 32, lo);
-          }
-          tmem_st_wait();
-          tc_fence_before();
-        }
-      } else {
 #pragma unroll 1
       for (int kc = 0; restage && kc < Cfg::kKC; ++kc) {
         float4 v[8];
@@ -246,7 +217,6 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
           *reinterpret_cast<float4*>(hi + off) = h;
           *reinterpret_cast<float4*>(hi + kPackImageBytes + off) = l;
         }
-      }
       }
       if (restage) {
         fence_async_smem();
@@ -282,8 +252,8 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
       }
       tc_fence_after();
       for (int oi = 0; oi < oc; ++oi, ++ocount) {
-        const uint32_t b = kTS ? 0u : (ocount & 1u);
-        mbar_wait(&tmem_empty[b], ((kTS ? ocount : (ocount >> 1)) + 1) & 1u);
+        const uint32_t b = ocount & 1u;
+        mbar_wait(&tmem_empty[b], ((ocount >> 1) + 1) & 1u);
         tc_fence_after();
         for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
           const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
@@ -296,22 +266,13 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
             // columns [d, d+F) receive a_hi*b_hi (main), [d+F, d+2F) a_hi*b_lo (correction); a second N = F MMA adds
             // a_lo*b_hi to the correction columns.  Two instructions and 20 KB of shared-memory operand reads per
             // K step instead of three and 24 KB — with M = N = 128 operand tiles the SS-mode MMAs run at the
-            // shared-memory bandwidth limit, not at the tensor pipe's.  (kTS: A from tensor memory, 12 KB.)
-            if (kTS) {
+            // shared-memory bandwidth limit, not at the tensor pipe's.
+            const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t off = ks * 32, ka = kc * 32 + ks * 8;
-                umma_tf32_ts(d, tmem + kAHiCol + ka, umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
-                umma_tf32_ts(dc, tmem + kALoCol + ka, umma_desc_k_sw128(b_hi + off), idesc, 1);
-              }
-            } else {
-              const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
-#pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                const uint32_t off = ks * 32;
-                umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
-                umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
-              }
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t off = ks * 32;
+              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
             }
             umma_commit(&empty[s]);
             if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);
@@ -337,33 +298,21 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
 using namespace cgat;
 
 namespace {
-template <int kMode, bool kTS>
+template <int kMode>
 int launch_hyper_impl(const float* z, const float* y_in, const float* e_term, const float* e_term2, const float* w_bias,
                       const float* w_packed, float* y_out, int64_t n_atoms, int32_t f, cudaStream_t stream) {
-  using Cfg = HyperCfg<128, kTS>;
+  using Cfg = HyperCfg<128>;
   static bool configured = false;
   if (!configured) {
-    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_fwd_kernel<128, kMode, kTS>,
+    CGAT_CUDA(cudaFuncSetAttribute(hyper_rowdot_fwd_kernel<128, kMode>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
   }
   const int oc = hyper_chunk(n_atoms, f);
   const int grid = hyper_grid(n_atoms, f, kMode);
-  hyper_rowdot_fwd_kernel<128, kMode, kTS><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
+  hyper_rowdot_fwd_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
       z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f));
   return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");
-}
-
-// Default: z tile in shared memory (SS-mode MMAs, double-buffered accumulators).  CGAT_B200_HYPER_TS=1 selects the
-// variant with the z tile in tensor memory (TS-mode MMAs, single accumulator buffer): numerically identical and
-// parity-tested, but measured SLOWER on B200 at the bench size (140 vs 112 us backward, 166 vs 130 us forward per
-// launch) — losing the accumulator double buffer costs more than the saved shared-memory operand reads.
-bool hyper_ts() {
-  static const bool on = [] {
-    const char* e = getenv("CGAT_B200_HYPER_TS");
-    return e && e[0] == '1';
-  }();
-  return on;
 }
 
 template <int kMode>
@@ -372,9 +321,7 @@ int launch_hyper(const float* z, const float* y_in, const float* e_term, const f
   if (n_atoms <= 0) return 0;
   if (f != 128) return fail(-2, "cgat_hyper_*: only F = 128 is instantiated");
   if (n_atoms >= (1ll << 31) - 128) return fail(-2, "cgat_hyper_*: too many atoms");
-  if (hyper_ts())
-    return launch_hyper_impl<kMode, true>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, f, stream);
-  return launch_hyper_impl<kMode, false>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, f, stream);
+  return launch_hyper_impl<kMode>(z, y_in, e_term, e_term2, w_bias, w_packed, y_out, n_atoms, f, stream);
 }
 }  // namespace
 

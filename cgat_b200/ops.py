@@ -813,8 +813,12 @@ def edge_attention(x, edge_table, plan, mh_a, mh_m, heads, edge_ids=None):
     the destination-sorted order; that variant runs the unfused formulation (the fused kernel gathers a per-rank table)."""
     f = x.shape[1]
     hd = mh_a.hidden_dim
-    base_ok = (_FUSED and edge_ids is None and x.is_cuda and mh_a.output_dim == f and mh_m.output_dim == f
-               and heads <= 8 and edge_table.shape[1] % 4 == 0 and edge_table.shape[0] <= 32)
+    # scalar attention (vector_attention=False, reference CGAT/CGAT.py:282-287: the gate net emits ONE logit per head
+    # that weighs all channels): run as vector attention whose gate rows are that one row repeated — `expand` is an
+    # autograd op, so the F per-channel gate gradients the kernels produce are summed back onto the single row
+    scalar_gate = mh_a.output_dim == 1 and f > 1
+    base_ok = (_FUSED and edge_ids is None and x.is_cuda and (mh_a.output_dim == f or scalar_gate)
+               and mh_m.output_dim == f and heads <= 8 and edge_table.shape[1] % 4 == 0 and edge_table.shape[0] <= 32)
     # the original instantiation: F = 128, whole 128-unit hidden tiles (tf32 kernels, or f16 forward + either backward)
     small_ok = base_ok and f == 128 and hd % 128 == 0 and hd <= 256
     # generalised f16 path (BASELINE.json configs[3]: F = 256, 8 heads, Hd = 426): F in {128, 256} run as F / 128
@@ -825,9 +829,13 @@ def edge_attention(x, edge_table, plan, mh_a, mh_m, heads, edge_ids=None):
     if small_ok or wide_ok:
         f16 = (_F16X3_EDGE and hd % 64 == 0) if small_ok else True
         pk = dict(f16=True, pre_scale=_EDGE_W2_PRESCALE) if f16 else {}
-        out = _EdgeAttentionFused.apply(x, edge_table, mh_a.fc_in.weight, mh_a.fc_in.bias, mh_a.fc_out.weight,
-                                        mh_a.fc_out.bias, mh_m.fc_in.weight, mh_m.fc_in.bias, mh_m.fc_out.weight,
-                                        mh_m.fc_out.bias, packed_kmajor(mh_a.fc_out.weight, **pk),
+        w2a, b2a = mh_a.fc_out.weight, mh_a.fc_out.bias
+        if scalar_gate:
+            w2a = w2a.view(heads, 1, hd, 1).expand(heads, f, hd, 1).reshape(heads * f, hd, 1)
+            b2a = b2a.view(heads, 1).expand(heads, f).reshape(heads * f)
+        out = _EdgeAttentionFused.apply(x, edge_table, mh_a.fc_in.weight, mh_a.fc_in.bias, w2a, b2a,
+                                        mh_m.fc_in.weight, mh_m.fc_in.bias, mh_m.fc_out.weight,
+                                        mh_m.fc_out.bias, packed_kmajor(w2a, **pk),
                                         packed_kmajor(mh_m.fc_out.weight, **pk), plan, heads, f16,
                                         hd_pad if f16 else hd)
         return out.mean(dim=1)

@@ -248,7 +248,17 @@ def test_edge_attention_fused_wide(n_cry, k, heads, lo, hi, f):
     assert _lib.launch_count() - before >= 10
 
 
-def _edge_backward_case(n_cry, k, heads, lo, hi, f, kink_tolerant_table=False):
+@pytest.mark.parametrize("n_cry,k,heads,f", [(40, 12, 5, 128), (25, 12, 4, 256)])
+def test_edge_attention_fused_scalar_gate(n_cry, k, heads, f):
+    """vector_attention=False (reference CGAT/CGAT.py:282-287: one gate logit per head) on the fused kernels: the gate
+    row is repeated over the channels through an autograd `expand`, so the kernels run unchanged and the per-channel
+    gate gradients are summed back onto the single row.  Forward and every gradient against the fp64 restatement."""
+    before = _lib.launch_count()
+    _edge_backward_case(n_cry, k, heads, 2, 20, f, kink_tolerant_table=True, scalar_gate=True)
+    assert _lib.launch_count() - before >= 10
+
+
+def _edge_backward_case(n_cry, k, heads, lo, hi, f, kink_tolerant_table=False, scalar_gate=False):
     from cgat_b200.CGAT import MultiHeadNetwork
     from tests._cases import assert_grad_close
     fe = 128
@@ -257,7 +267,7 @@ def _edge_backward_case(n_cry, k, heads, lo, hi, f, kink_tolerant_table=False):
     n = gidx.num_nodes
     torch.manual_seed(n_cry)
     width = 2 * f + fe
-    mh_a = MultiHeadNetwork(width, f, int(width / 1.5), heads)
+    mh_a = MultiHeadNetwork(width, 1 if scalar_gate else f, int(width / 1.5), heads)
     mh_m = MultiHeadNetwork(width, f, int(width / 1.5), heads)
     x = torch.randn(n, f) * 0.5
     tab = torch.randn(k + 1, fe)
