@@ -312,7 +312,10 @@ def _edge_backward_case(n_cry, k, heads, lo, hi, f, kink_tolerant_table=False, s
         for kk, p in mod.named_parameters():
             ref_g = sd[pre + kk].grad
             scale = max(ref_g.abs().max().item(), 1e-3)
-            assert_grad_close(p.grad, ref_g, f"d_{pre}{kk}", atol=1e-4 + 1e-5 * scale)
+            # a scalar gate's hidden units carry the gradient of all 128 channels at once: when one pre-activation sits
+            # on the LeakyReLU kink, that unit's bias / weight-row gradient moves by a larger share of the maximum
+            assert_grad_close(p.grad, ref_g, f"d_{pre}{kk}", atol=1e-4 + 1e-5 * scale,
+                              outlier_cap=5e-2 if scalar_gate else 2e-2)
     # deterministic
     xc2 = x.to(DEV).requires_grad_(True)
     for p in list(mh_a.parameters()) + list(mh_m.parameters()):
