@@ -13,8 +13,8 @@ import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # CGAT_B200_LIB=trap selects the debug build whose mbarrier waits are bounded (python -m cgat_b200.build --trap-barriers)
-LIB_PATH = os.path.join(_HERE, "libcgat_b200_trap.so" if os.environ.get("CGAT_B200_LIB") == "trap"
-                        else "libcgat_b200.so")
+_VARIANT = os.environ.get("CGAT_B200_LIB", "")
+LIB_PATH = os.path.join(_HERE, f"libcgat_b200_{_VARIANT}.so" if _VARIANT else "libcgat_b200.so")
 _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t

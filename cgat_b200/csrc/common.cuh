@@ -65,19 +65,33 @@ inline int hyper_chunk(int64_t n_atoms, int f) {
 // (this CTA) - (first CTA that touches the tile).  hyper_slots() bounds that slot count: with >= per = floor(items /
 // grid) items per CTA a tile's n_chunks items meet at most ceil(n_chunks / per) + 1 CTAs.  (Round 1 wrote one partial
 // per chunk: 16 x N x F floats per launch at the bench size instead of 5, all re-read by the partial sum.)
-inline int64_t hyper_items(int64_t n_atoms, int f, int mode) {
-  // forward (mode 0): (atom tile, output chunk); backward (mode 1): ((atom tile, 128-column half), output chunk)
-  return ((n_atoms + 127) / 128) * (mode ? f / 128 : 1) * (f / hyper_chunk(n_atoms, f));
+#ifndef CGAT_HYPER_CLUSTER
+#define CGAT_HYPER_CLUSTER 2
+#endif
+constexpr int kHyperCluster = CGAT_HYPER_CLUSTER;   // CTAs per cluster of the f16 hyper kernels: they share every weight stage by multicast
+
+inline int64_t hyper_items(int64_t n_atoms, int f, int mode, int cs = 1) {
+  // forward (mode 0): (atom tile group, output chunk); backward (mode 1): ((tile group, 128-column half), output chunk);
+  // a tile group = the `cs` consecutive atom tiles that the CTAs of one cluster work on side by side
+  const int64_t n_tg = ((n_atoms + 127) / 128 + cs - 1) / cs;
+  return n_tg * (mode ? f / 128 : 1) * (f / hyper_chunk(n_atoms, f));
 }
-inline int hyper_grid(int64_t n_atoms, int f, int mode = 0) {
-  const int64_t n_items = hyper_items(n_atoms, f, mode);
-  return (int)(n_items < kNumSMs ? (n_items > 0 ? n_items : 1) : kNumSMs);
+// number of CTAs (cs = 1) or clusters (cs > 1) of the launch
+inline int hyper_grid(int64_t n_atoms, int f, int mode = 0, int cs = 1) {
+  const int64_t n_items = hyper_items(n_atoms, f, mode, cs);
+  const int cap = kNumSMs / cs;
+  return (int)(n_items < cap ? (n_items > 0 ? n_items : 1) : cap);
 }
-inline int hyper_slots(int64_t n_atoms, int f) {
+inline int hyper_slots(int64_t n_atoms, int f, int cs = 1) {
   const int n_chunks = f / hyper_chunk(n_atoms, f);
-  const int64_t per = hyper_items(n_atoms, f, 1) / hyper_grid(n_atoms, f, 1);
+  const int64_t per = hyper_items(n_atoms, f, 1, cs) / hyper_grid(n_atoms, f, 1, cs);
   const int64_t s = per > 0 ? (n_chunks + per - 1) / per + 1 : n_chunks;
   return (int)(s < n_chunks ? s : n_chunks);
+}
+// partial-result slots the caller allocates: enough for the tf32 kernel (no clusters) and the f16 kernel (clusters)
+inline int hyper_parts(int64_t n_atoms, int f) {
+  const int a = hyper_slots(n_atoms, f, 1), b = hyper_slots(n_atoms, f, kHyperCluster);
+  return a > b ? a : b;
 }
 // first CTA whose item range [n_items*b/G, n_items*(b+1)/G) contains item i
 __host__ __device__ inline int hyper_cta_of_item(int64_t i, int64_t n_items, int G) {

@@ -67,18 +67,26 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_free + 1);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // A cluster of kCS CTAs works on kCS consecutive atom tiles (a "tile group") side by side and walks the SAME
+  // sequence of weight stages: the leader CTA fetches every 32 KB stage ONCE from L2 and the copy engine multicasts it
+  // into the same shared-memory offset of every CTA of the cluster (the weight stream from L2, 64 KB per output channel
+  // and CTA, was what the MMA warp waited for: ncu r02y, 45 % of all samples on the epilogue's wait for the accumulator).
+  constexpr int kCS = kHyperCluster;
+  const int crank = (int)cluster_ctarank();
+  const int cid = (int)blockIdx.x / kCS, n_clusters = (int)gridDim.x / kCS;
   const int n_tiles = (n_atoms + 127) / 128;
+  const int n_tg = (n_tiles + kCS - 1) / kCS;
   const int n_chunks = F / oc;
-  const int n_vt = kMode == 0 ? n_tiles : n_tiles * NH;   // (virtual) tiles: backward splits a tile into its column halves
+  const int n_vt = kMode == 0 ? n_tg : n_tg * NH;   // (virtual) tile groups: backward splits a tile into its column halves
   const int n_items = n_vt * n_chunks;
-  // work item = ((virtual) atom tile, chunk of output channels), chunk fastest; contiguous item range per CTA
-  const int item_lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x);
-  const int item_hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
+  // work item = ((virtual) tile group, chunk of output channels), chunk fastest; contiguous item range per CLUSTER
+  const int item_lo = (int)((int64_t)n_items * cid / n_clusters);
+  const int item_hi = (int)((int64_t)n_items * (cid + 1) / n_clusters);
 
   if (tid == 0) {
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], kCS);   // the MMAs of EVERY CTA of the cluster have read the stage
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full[b], 1);
@@ -92,6 +100,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
   if (warp == kMmaWarp) tmem_alloc(tmem_slot, Cfg::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  cluster_sync_all();   // every CTA's barriers are initialised before anyone multicasts into / arrives on them
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
@@ -110,7 +119,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     float sc_max = 0.f;   // kMode 1: max |scale| seen by this thread (the gradient operand of the weight-gradient kernel)
     for (int item = item_lo; item < item_hi; ++item) {
       const int vt = item / n_chunks, chunk = item - vt * n_chunks;
-      const int tile = kMode == 0 ? vt : vt / NH, vhalf = kMode == 0 ? 0 : vt % NH;
+      const int tile = (kMode == 0 ? vt : vt / NH) * kCS + crank, vhalf = kMode == 0 ? 0 : vt % NH;
       const int n = tile * 128 + row;
       const bool valid = n < n_atoms;
       for (int hh = 0; hh < kHalvesPerItem; ++hh) {
@@ -126,10 +135,14 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
             y[4 * j] = t.x, y[4 * j + 1] = t.y, y[4 * j + 2] = t.z, y[4 * j + 3] = t.w;
           }
         }
+        // kMode 1: the scale g[n, o] of output o+1 is requested while output o is consumed — a dependent global load
+        // right behind the accumulator barrier was an exposed L2 round trip per output channel
+        float sc_next = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + chunk * oc) : 0.f;
         for (int oi = 0; oi < oc; ++oi, ++ocount) {
           const int o = chunk * oc + oi;
           const uint32_t b = ocount & 1u;
-          const float sc = (kMode == 1 && valid) ? __ldg(y_in + (int64_t)n * F + o) : 0.f;
+          const float sc = sc_next;
+          if (kMode == 1 && valid && oi + 1 < oc) sc_next = __ldg(y_in + (int64_t)n * F + o + 1);
           if (kMode == 1) sc_max = fmaxf(sc_max, fabsf(sc));
           // The bias of the predicted weight row, p[n, o*F + j] = D_o[n, j] + bl[o*F + j], does not depend on the MMAs:
           // its contribution is taken BEFORE waiting for the accumulator (broadcast loads: every thread of a column
@@ -203,7 +216,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
       if (kMode == 1 && valid && (item + 1 == item_hi || chunk == n_chunks - 1)) {
         // end of this CTA's run on the (virtual) tile: one partial per (CTA, tile); the CTA that finishes the tile also
         // clears the slots nobody used (the caller sums all n_slots)
-        const int slot = (int)blockIdx.x - hyper_cta_of_item((int64_t)vt * n_chunks, n_items, (int)gridDim.x);
+        const int slot = cid - hyper_cta_of_item((int64_t)vt * n_chunks, n_items, n_clusters);
         const int64_t col = vhalf * 128 + grp * QF;
         float4* dst = reinterpret_cast<float4*>(y_out + ((int64_t)slot * n_atoms + n) * F + col);
 #pragma unroll
@@ -232,7 +245,7 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     int staged_tile = -1;
     for (int item = item_lo; item < item_hi; ++item) {
       const int vt = item / n_chunks, chunk = item - vt * n_chunks;
-      const int tile = kMode == 0 ? vt : vt / NH, vhalf = kMode == 0 ? 0 : vt % NH;
+      const int tile = (kMode == 0 ? vt : vt / NH) * kCS + crank, vhalf = kMode == 0 ? 0 : vt % NH;
       const bool restage = tile != staged_tile;
       staged_tile = tile;
       if (restage) mbar_wait(a_free, (it + 1) & 1u);  // the previous tile's MMAs have finished reading the tile
@@ -278,10 +291,14 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
             const int64_t rt = (int64_t)(chunk * oc + oi) * NH + half;   // 128-row tile of the packed weight
             for (int kc = 0; kc < Cfg::kKC; ++kc, ++cnt) {
               const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
-              mbar_wait(&empty[s], (u + 1) & 1u);
+              mbar_wait(&empty[s], (u + 1) & 1u);   // all CTAs of the cluster are done with the stage's last contents
               mbar_arrive_expect_tx(&full[s], kPackStageBytes);
-              bulk_g2s(b_smem + s * kPackStageBytes, wsrc + (rt * Cfg::kKC + kc) * kPackStageBytes, kPackStageBytes,
-                       &full[s]);
+              if constexpr (kCS == 1)
+                bulk_g2s(b_smem + s * kPackStageBytes, wsrc + (rt * Cfg::kKC + kc) * kPackStageBytes, kPackStageBytes,
+                         &full[s]);
+              else if (crank == 0)
+                bulk_g2s_multicast(b_smem + s * kPackStageBytes, wsrc + (rt * Cfg::kKC + kc) * kPackStageBytes,
+                                   kPackStageBytes, &full[s], (uint16_t)((1u << kCS) - 1));
             }
           }
         }
@@ -293,9 +310,11 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
     constexpr uint32_t idesc = umma_idesc_f16(128, 128), idesc2 = umma_idesc_f16(128, 256);
     uint32_t it = 0, cnt = 0, ocount = 0;
     int staged_tile = -1;
+    // (A second issuing warp, one per accumulator buffer, was measured: no change — after the converged issue below the
+    // kernel is paced by the tensor pipe's operand path, not by the issuing thread.)
     for (int item = item_lo; item < item_hi; ++item) {
       const int vt = item / n_chunks;
-      const int tile = kMode == 0 ? vt : vt / NH;
+      const int tile = kMode == 0 ? vt : vt / NH;   // tile GROUP: this CTA's tile is tile * kCS + crank
       if (tile != staged_tile) {
         mbar_wait(a_full, it & 1u);
         ++it;
@@ -310,31 +329,35 @@ hyper_rowdot_f16_kernel(const float* __restrict__ z, const float* __restrict__ y
           const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
           mbar_wait(&full[s], u & 1u);
           tc_fence_after();
-          if (lane == 0) {
+          {
+            // all 32 lanes, warp-uniform operands; one elected lane issues (tc_common.cuh, "_e" forms)
             const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes);
             const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
             const uint32_t d = tmem + b * 256, dc = d + 128;
             // one N = 256 MMA multiplies a_hi with the adjacent [b_hi; b_lo] images (main | correction columns), one
             // N = 128 MMA adds a_lo * b_hi to the correction columns; each K step is 16 halves = 32 bytes of the row
+            const uint64_t da_hi = umma_desc_k_sw128(a_hi), da_lo = umma_desc_k_sw128(a_lo), db = umma_desc_k_sw128(b_hi);
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
-              const uint32_t off = ks * 32;
-              umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
-              umma_f16(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+              const uint64_t off = (uint64_t)(ks * 2);   // 32 bytes along the swizzled row = 2 units of the address field
+              umma_f16_e(d, da_hi + off, db + off, idesc2, (kc | ks) != 0);
+              umma_f16_e(dc, da_lo + off, db + off, idesc, 1);
             }
-            umma_commit(&empty[s]);
-            if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);
+            if constexpr (kCS == 1) umma_commit_e(&empty[s]);
+            else umma_commit_multicast_e(&empty[s], (uint16_t)((1u << kCS) - 1));
+            if (kc == Cfg::kKC - 1) umma_commit_e(&tmem_full[b]);
           }
           __syncwarp();
         }
       }
       // last item of this atom tile: the activation tile may be overwritten once these MMAs are done
       const int next_tile = item + 1 == item_hi ? -1 : (kMode == 0 ? (item + 1) / n_chunks : (item + 1) / n_chunks / NH);
-      if (next_tile != tile && lane == 0) umma_commit(a_free);
+      if (next_tile != tile) umma_commit_e(a_free);
       __syncwarp();
     }
   }
   __syncthreads();
+  cluster_sync_all();   // nobody leaves while a peer may still multicast into its shared memory or arrive on its barriers
   if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, Cfg::kTmemCols);
@@ -358,10 +381,36 @@ int launch_hyper16_f(const float* z, const float* y_in, const float* e_term, con
     configured = true;
   }
   const int oc = hyper_chunk(n_atoms, F);
-  const int grid = hyper_grid(n_atoms, F, kMode);
-  hyper_rowdot_f16_kernel<F, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, F),
-      reinterpret_cast<unsigned int*>(scale_amax));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)kNumSMs);
+  cfg.blockDim = dim3((unsigned)Cfg::kThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kHyperCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  // a cluster needs its CTAs on SMs of one GPC: GPCs with an odd number of SMs leave one unpaired, so fewer than
+  // 148 / 2 clusters can be resident at once — a persistent grid must not exceed that or its tail runs as a second wave
+  static int max_clusters = 0;
+  if (max_clusters == 0) {
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, hyper_rowdot_f16_kernel<F, kMode>, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = kNumSMs / kHyperCluster - 4;
+    }
+    max_clusters = n;
+  }
+  int n_clusters = hyper_grid(n_atoms, F, kMode, kHyperCluster);
+  if (n_clusters > max_clusters) n_clusters = max_clusters;
+  cfg.gridDim = dim3((unsigned)(n_clusters * kHyperCluster));
+  const int n_atoms_i = (int)n_atoms, n_slots = hyper_parts(n_atoms, F);
+  unsigned int* amax = reinterpret_cast<unsigned int*>(scale_amax);
+  CGAT_CUDA(cudaLaunchKernelEx(&cfg, hyper_rowdot_f16_kernel<F, kMode>, z, y_in, e_term, e_term2, w_bias, w_packed, y_out,
+                               n_atoms_i, oc, n_slots, amax));
   return check_launch(kMode == 0 ? "hyper_rowdot_f16_kernel" : "hyper_rowscale_f16_kernel");
 }
 

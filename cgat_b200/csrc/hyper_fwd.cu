@@ -311,7 +311,7 @@ int launch_hyper_impl(const float* z, const float* y_in, const float* e_term, co
   const int oc = hyper_chunk(n_atoms, f);
   const int grid = hyper_grid(n_atoms, f, kMode);
   hyper_rowdot_fwd_kernel<128, kMode><<<grid, Cfg::kThreads, Cfg::kSmemBytes, stream>>>(
-      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_slots(n_atoms, f));
+      z, y_in, e_term, e_term2, w_bias, w_packed, y_out, (int)n_atoms, oc, hyper_parts(n_atoms, f));
   return check_launch(kMode == 0 ? "hyper_rowdot_fwd_kernel" : "hyper_rowscale_kernel");
 }
 
@@ -336,7 +336,7 @@ extern "C" int cgat_hyper_rowdot_fwd(const float* z, const float* y_in, const fl
 }
 
 // number of partial results cgat_hyper_rowscale writes for this problem size
-extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { return hyper_slots(n_atoms, f); }
+extern "C" int32_t cgat_hyper_rowscale_parts(int64_t n_atoms, int32_t f) { return hyper_parts(n_atoms, f); }
 
 // partial[c][n,j] = sum_{o in chunk c} scale[n,o] * (sum_m a[n,m] Wblk_o[j,m] + w_bias[o*F+j]);  sum over c = the
 // result (w_bias optional: the bias of the predicted weights when a = z, NULL when a = y).

@@ -269,6 +269,34 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
       : "memory");
 }
 
+// ---- thread-block clusters: multicast of a pre-packed operand stage to every CTA of the cluster ------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// global -> the SAME shared-memory offset in every CTA of `cta_mask`; each destination CTA's mbarrier at the offset of
+// `bar` receives complete_tx(bytes) (SASS: UBLKCP with .MULTICAST).  One L2 read feeds all CTAs of the cluster.
+__device__ __forceinline__ void bulk_g2s_multicast(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "h"(cta_mask)
+      : "memory");
+}
+// tcgen05.commit that arrives on the mbarrier at the offset of `bar` in every CTA of `cta_mask`: "this CTA's MMAs have
+// finished reading the stage" reaches the CTA that refills it for the whole cluster (and the others, which re-arm)
+__device__ __forceinline__ void umma_commit_multicast(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"(cta_mask)
+               : "memory");
+}
+
 // Packed K-major operand: a [rows x k] fp32 matrix cut into tiles of kPackRows rows x 32 floats, each
 // stored as two consecutive 16 KB SWIZZLE_128B images (tf32 hi, then tf32 lo) in the order
 // [row_tile][k_chunk][hi|lo].  One bulk copy of 32 KB brings a ready-to-multiply stage.
@@ -307,6 +335,50 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t desc_a, uint6
       ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- warp-converged issue ("_e" forms) --------------------------------------------------------------------------
+// tcgen05.mma / tcgen05.commit take their operands from UNIFORM registers.  Issued from inside `if (lane == 0)` the
+// compiler cannot use the uniform datapath and wraps EVERY instruction in an elect / R2UR.BROADCAST / branch loop
+// (≈ 15 instructions and a back edge per MMA: ncu r02y showed the issuing warp never waiting on a barrier while the
+// tensor pipe sat at half rate — the issue loop itself was the pace).  These forms are called by ALL 32 lanes of the
+// converged MMA warp with warp-uniform arguments; one lane, chosen by elect.sync inside the asm (always the same lane
+// of a converged warp, so tcgen05.commit tracks the MMAs that lane issued), executes the instruction.
+__device__ __forceinline__ void umma_f16_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_tf32_e(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_e(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast_e(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
+      : "memory");
+}
+
 // two fp32 -> packed (hi.x | hi.y << 16), (lo.x | lo.y << 16), lo = rn_f16((x - hi) * lo_scale)
 // hi is taken as the fp32 value rounded to 11 significant bits on the bit pattern (round_tf32: fp16 and tf32 carry the
 // same 11 bits), which IS the fp16 value whenever x lies in fp16's normal range, so no half -> float conversion is
