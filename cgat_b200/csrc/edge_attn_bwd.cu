@@ -419,24 +419,24 @@ __global__ void __launch_bounds__(kDThreads, 1) edge_dgrad_kernel(const DgradArg
           const uint32_t s = cnt % kBStages, u = cnt / kBStages;
           mbar_wait(&full[s], u & 1u);
           tc_fence_after();
-          if (lane == 0) {
+          {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
             const uint32_t a_hi = smem_u32(stages + s * kBStageBytes), a_lo = a_hi + kPackImageBytes;
             const uint32_t b_hi = a_hi + kPackStageBytes, b_lo = b_hi + kPackImageBytes;
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
               if constexpr (kF16) {
-                umma_f16(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-                umma_f16(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-                umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                umma_f16_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                umma_f16_e(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
               } else {
-                umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-                umma_tf32(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-                umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                umma_tf32_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                umma_tf32_e(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                umma_tf32_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
               }
             }
-            umma_commit(&empty[s]);
-            if (kc == kcf - 1) umma_commit(&tmem_full[b]);
+            umma_commit_e(&empty[s]);
+            if (kc == kcf - 1) umma_commit_e(&tmem_full[b]);
           }
           __syncwarp();
         }
@@ -589,20 +589,20 @@ __global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArg
       const int s = ch % kWStages, u = ch / kWStages;
       mbar_wait(&full[s], u & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t a_hi = smem_u32(stages + s * kWStageBytes), a_lo = a_hi + kWAPart;
         const uint32_t b_hi = a_hi + 2 * kWAPart, b_lo = b_hi + kWBPart;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
           const uint32_t o = ks * 1024;
-          umma_tf32(tmem + 256, umma_desc_mn_sw128(a_lo + o, kWImage), umma_desc_mn_sw128(b_hi + o, kWImage), idesc,
+          umma_tf32_e(tmem + 256, umma_desc_mn_sw128(a_lo + o, kWImage), umma_desc_mn_sw128(b_hi + o, kWImage), idesc,
                     (ch | ks) != 0);
-          umma_tf32(tmem + 256, umma_desc_mn_sw128(a_hi + o, kWImage), umma_desc_mn_sw128(b_lo + o, kWImage), idesc, 1);
-          umma_tf32(tmem, umma_desc_mn_sw128(a_hi + o, kWImage), umma_desc_mn_sw128(b_hi + o, kWImage), idesc,
+          umma_tf32_e(tmem + 256, umma_desc_mn_sw128(a_hi + o, kWImage), umma_desc_mn_sw128(b_lo + o, kWImage), idesc, 1);
+          umma_tf32_e(tmem, umma_desc_mn_sw128(a_hi + o, kWImage), umma_desc_mn_sw128(b_hi + o, kWImage), idesc,
                     (ch | ks) != 0);
         }
-        umma_commit(&empty[s]);
-        if (ch == n_chunks - 1) umma_commit(accum);
+        umma_commit_e(&empty[s]);
+        if (ch == n_chunks - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }

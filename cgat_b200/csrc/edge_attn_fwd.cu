@@ -489,24 +489,24 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             const uint32_t s = cnt % kEStages, u = cnt / kEStages;
             mbar_wait(&full[s], u & 1u);
             tc_fence_after();
-            if (lane == 0) {
+            {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
               const uint32_t a_hi = smem_u32(stages + s * kEStageBytes), a_lo = a_hi + kPackImageBytes;
               const uint32_t b_hi = a_hi + kPackStageBytes, b_lo = b_hi + kPackImageBytes;
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t off = ks * 32;
                 if constexpr (kF16) {  // K = 16 halves = the same 32 bytes of the swizzled row
-                  umma_f16(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-                  umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-                  umma_f16(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+                  umma_f16_e(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                  umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                  umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
                 } else {
-                  umma_tf32(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-                  umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-                  umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+                  umma_tf32_e(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+                  umma_tf32_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+                  umma_tf32_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
                 }
               }
-              umma_commit(&empty[s]);
-              if (net == 1 && kc == kcn - 1) umma_commit(&tmem_full[hb]);
+              umma_commit_e(&empty[s]);
+              if (net == 1 && kc == kcn - 1) umma_commit_e(&tmem_full[hb]);
             }
             __syncwarp();
           }

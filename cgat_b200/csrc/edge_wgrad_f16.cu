@@ -185,20 +185,20 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
       const int st = ch % kWStagesN, u = ch / kWStagesN;
       mbar_wait(&full[st], u & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t a_hi = smem_u32(stages + st * kWStage), a_lo = a_hi + kWA;
         const uint32_t b_hi = a_hi + 2 * kWA, b_lo = b_hi + kWB;
 #pragma unroll
         for (int ks = 0; ks < kWRows / 16; ++ks) {
           const uint32_t o = ks * 2048;
-          umma_f16(tmem + 256, umma_desc_mn_sw128_16b(a_lo + o, kWImg), umma_desc_mn_sw128_16b(b_hi + o, kWImg), idesc,
+          umma_f16_e(tmem + 256, umma_desc_mn_sw128_16b(a_lo + o, kWImg), umma_desc_mn_sw128_16b(b_hi + o, kWImg), idesc,
                    (ch | ks) != 0);
-          umma_f16(tmem + 256, umma_desc_mn_sw128_16b(a_hi + o, kWImg), umma_desc_mn_sw128_16b(b_lo + o, kWImg), idesc, 1);
-          umma_f16(tmem, umma_desc_mn_sw128_16b(a_hi + o, kWImg), umma_desc_mn_sw128_16b(b_hi + o, kWImg), idesc,
+          umma_f16_e(tmem + 256, umma_desc_mn_sw128_16b(a_hi + o, kWImg), umma_desc_mn_sw128_16b(b_lo + o, kWImg), idesc, 1);
+          umma_f16_e(tmem, umma_desc_mn_sw128_16b(a_hi + o, kWImg), umma_desc_mn_sw128_16b(b_hi + o, kWImg), idesc,
                    (ch | ks) != 0);
         }
-        umma_commit(&empty[st]);
-        if (ch == n_chunks - 1) umma_commit(accum);
+        umma_commit_e(&empty[st]);
+        if (ch == n_chunks - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }

@@ -162,7 +162,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
       const int s = kc % S::kStages, u = kc / S::kStages;
       mbar_wait(&full[s], u & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t a_hi = smem_u32(smem + s * S::kStageBytes);
         const uint32_t a_lo = a_hi + S::kABytes;
         const uint32_t b_hi = a_hi + 2 * S::kABytes;
@@ -170,12 +170,12 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 #pragma unroll
         for (int ks = 0; ks < kKC / 8; ++ks) {  // UMMA K = 8 tf32 = 32 bytes along the swizzled row
           const uint32_t o = ks * 32;
-          umma_tf32(tmem + BN, umma_desc_k_sw128(a_lo + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
-          umma_tf32(tmem + BN, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_lo + o), idesc, 1);
-          umma_tf32(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
+          umma_tf32_e(tmem + BN, umma_desc_k_sw128(a_lo + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
+          umma_tf32_e(tmem + BN, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_lo + o), idesc, 1);
+          umma_tf32_e(tmem, umma_desc_k_sw128(a_hi + o), umma_desc_k_sw128(b_hi + o), idesc, (kc | ks) != 0);
         }
-        umma_commit(&empty[s]);  // stage reusable once these MMAs have read it
-        if (kc == nk - 1) umma_commit(accum);
+        umma_commit_e(&empty[s]);  // stage reusable once these MMAs have read it
+        if (kc == nk - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }
@@ -312,20 +312,20 @@ gemm3x_tn_kernel(const TnArgs g) {
       const int s = kc % kStages, u = kc / kStages;
       mbar_wait(&full[s], u & 1);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t a_hi = smem_u32(smem + s * kStageBytes), a_lo = a_hi + kOp;
         const uint32_t b_hi = a_hi + 2 * kOp, b_lo = a_hi + 3 * kOp;
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {  // one MMA consumes 8 K-rows = two 512-byte atoms of every image
           const uint32_t o = ks * 1024;
-          umma_tf32(tmem + 128, umma_desc_mn_sw128(a_lo + o, kTnImage), umma_desc_mn_sw128(b_hi + o, kTnImage), idesc,
+          umma_tf32_e(tmem + 128, umma_desc_mn_sw128(a_lo + o, kTnImage), umma_desc_mn_sw128(b_hi + o, kTnImage), idesc,
                     (kc | ks) != 0);
-          umma_tf32(tmem + 128, umma_desc_mn_sw128(a_hi + o, kTnImage), umma_desc_mn_sw128(b_lo + o, kTnImage), idesc, 1);
-          umma_tf32(tmem, umma_desc_mn_sw128(a_hi + o, kTnImage), umma_desc_mn_sw128(b_hi + o, kTnImage), idesc,
+          umma_tf32_e(tmem + 128, umma_desc_mn_sw128(a_hi + o, kTnImage), umma_desc_mn_sw128(b_lo + o, kTnImage), idesc, 1);
+          umma_tf32_e(tmem, umma_desc_mn_sw128(a_hi + o, kTnImage), umma_desc_mn_sw128(b_hi + o, kTnImage), idesc,
                     (kc | ks) != 0);
         }
-        umma_commit(&empty[s]);
-        if (kc == nk - 1) umma_commit(accum);
+        umma_commit_e(&empty[s]);
+        if (kc == nk - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }

@@ -181,7 +181,7 @@ gemm3x_nt_res_kernel(const float* __restrict__ A, int64_t lda, const float* __re
         const uint32_t s = cnt % kRStages, u = cnt / kRStages;
         mbar_wait(&full[s], u & 1u);
         tc_fence_after();
-        if (lane == 0) {
+        {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
           const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
           const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes), b_lo = b_hi + kPackImageBytes;
           const uint32_t d = tmem + b * 256, dc = d + 128;
@@ -191,15 +191,15 @@ gemm3x_nt_res_kernel(const float* __restrict__ A, int64_t lda, const float* __re
             // one N = 256 MMA against the adjacent [hi | lo] weight images: a_hi*b_hi -> [d, d+128), a_hi*b_lo ->
             // [d+128, d+256); then a_lo*b_hi into the correction columns (see hyper_fwd.cu)
             const uint32_t off = ks * 32;
-            umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
-            umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+            umma_tf32_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+            umma_tf32_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
           }
-          umma_commit(&empty[s]);
-          if (kc == kcn - 1) umma_commit(&tmem_full[b]);
+          umma_commit_e(&empty[s]);
+          if (kc == kcn - 1) umma_commit_e(&tmem_full[b]);
         }
         __syncwarp();
       }
-      if ((item + 1 == item_hi || (item + 1) / n_tiles != mt) && lane == 0) umma_commit(a_free);
+      if ((item + 1 == item_hi || (item + 1) / n_tiles != mt)) umma_commit_e(a_free);
       __syncwarp();
     }
   }

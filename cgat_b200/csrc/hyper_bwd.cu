@@ -130,7 +130,7 @@ hyper_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ y, con
       const int s = ch % kHStages, u = ch / kHStages;
       mbar_wait(&full[s], u & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t z_hi = smem_u32(smem + s * kHStageBytes), z_lo = z_hi + kHPart;
 #pragma unroll
         for (int oo = 0; oo < 2; ++oo) {
@@ -139,15 +139,15 @@ hyper_wgrad_kernel(const float* __restrict__ g, const float* __restrict__ y, con
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t o = ks * 1024;
-            umma_tf32(d + 128, umma_desc_mn_sw128(a_lo + o, kHImage), umma_desc_mn_sw128(z_hi + o, kHImage), idesc,
+            umma_tf32_e(d + 128, umma_desc_mn_sw128(a_lo + o, kHImage), umma_desc_mn_sw128(z_hi + o, kHImage), idesc,
                       (ch | ks) != 0);
-            umma_tf32(d + 128, umma_desc_mn_sw128(a_hi + o, kHImage), umma_desc_mn_sw128(z_lo + o, kHImage), idesc, 1);
-            umma_tf32(d, umma_desc_mn_sw128(a_hi + o, kHImage), umma_desc_mn_sw128(z_hi + o, kHImage), idesc,
+            umma_tf32_e(d + 128, umma_desc_mn_sw128(a_hi + o, kHImage), umma_desc_mn_sw128(z_lo + o, kHImage), idesc, 1);
+            umma_tf32_e(d, umma_desc_mn_sw128(a_hi + o, kHImage), umma_desc_mn_sw128(z_hi + o, kHImage), idesc,
                       (ch | ks) != 0);
           }
         }
-        umma_commit(&empty[s]);
-        if (ch == n_chunks - 1) umma_commit(accum);
+        umma_commit_e(&empty[s]);
+        if (ch == n_chunks - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }

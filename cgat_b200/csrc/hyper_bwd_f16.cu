@@ -167,7 +167,7 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
       const int st = ch % kStagesW, u = ch / kStagesW;
       mbar_wait(&full[st], u & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t z_hi = smem_u32(smem + st * kStage), z_lo = z_hi + kPart;
 #pragma unroll
         for (int oo = 0; oo < 2; ++oo) {
@@ -176,15 +176,15 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
 #pragma unroll
           for (int ks = 0; ks < kRows / 16; ++ks) {   // one MMA consumes 16 K-rows = two 1024-byte groups of every image
             const uint32_t o = ks * 2048;
-            umma_f16(d + 128, umma_desc_mn_sw128_16b(a_lo + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
+            umma_f16_e(d + 128, umma_desc_mn_sw128_16b(a_lo + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
                      (ch | ks) != 0);
-            umma_f16(d + 128, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_lo + o, kImg), idesc, 1);
-            umma_f16(d, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
+            umma_f16_e(d + 128, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_lo + o, kImg), idesc, 1);
+            umma_f16_e(d, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
                      (ch | ks) != 0);
           }
         }
-        umma_commit(&empty[st]);
-        if (ch == n_chunks - 1) umma_commit(accum);
+        umma_commit_e(&empty[st]);
+        if (ch == n_chunks - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }
@@ -317,20 +317,20 @@ hyper_wgrad_f16_256_kernel(const float* __restrict__ g, const float* __restrict_
       const int st = ch % kStagesW, u = ch / kStagesW;
       mbar_wait(&full[st], u & 1u);
       tc_fence_after();
-      if (lane == 0) {
+      {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
         const uint32_t z_hi = smem_u32(smem + st * kStage2), z_lo = z_hi + kPartZ2;
         const uint32_t a_hi = z_hi + 2 * kPartZ2, a_lo = a_hi + kPart;
 #pragma unroll
         for (int ks = 0; ks < kRows / 16; ++ks) {
           const uint32_t o2 = ks * 2048;
-          umma_f16(tmem + 256, umma_desc_mn_sw128_16b(a_lo + o2, kImg), umma_desc_mn_sw128_16b(z_hi + o2, kImg), idesc,
+          umma_f16_e(tmem + 256, umma_desc_mn_sw128_16b(a_lo + o2, kImg), umma_desc_mn_sw128_16b(z_hi + o2, kImg), idesc,
                    (ch | ks) != 0);
-          umma_f16(tmem + 256, umma_desc_mn_sw128_16b(a_hi + o2, kImg), umma_desc_mn_sw128_16b(z_lo + o2, kImg), idesc, 1);
-          umma_f16(tmem, umma_desc_mn_sw128_16b(a_hi + o2, kImg), umma_desc_mn_sw128_16b(z_hi + o2, kImg), idesc,
+          umma_f16_e(tmem + 256, umma_desc_mn_sw128_16b(a_hi + o2, kImg), umma_desc_mn_sw128_16b(z_lo + o2, kImg), idesc, 1);
+          umma_f16_e(tmem, umma_desc_mn_sw128_16b(a_hi + o2, kImg), umma_desc_mn_sw128_16b(z_hi + o2, kImg), idesc,
                    (ch | ks) != 0);
         }
-        umma_commit(&empty[st]);
-        if (ch == n_chunks - 1) umma_commit(accum);
+        umma_commit_e(&empty[st]);
+        if (ch == n_chunks - 1) umma_commit_e(accum);
       }
       __syncwarp();
     }

@@ -259,7 +259,7 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
           const uint32_t s = cnt % Cfg::kStages, u = cnt / Cfg::kStages;
           mbar_wait(&full[s], u & 1u);
           tc_fence_after();
-          if (lane == 0) {
+          {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
             const uint32_t b_hi = smem_u32(b_smem + s * kPackStageBytes);
             const uint32_t d = tmem + b * 2 * F, dc = d + F;
             // The hi and lo images of a weight stage are adjacent, so ONE N = 2F MMA multiplies a_hi with both:
@@ -271,17 +271,17 @@ hyper_rowdot_fwd_kernel(const float* __restrict__ z, const float* __restrict__ y
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
-              umma_tf32(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
-              umma_tf32(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+              umma_tf32_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+              umma_tf32_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
             }
-            umma_commit(&empty[s]);
-            if (kc == Cfg::kKC - 1) umma_commit(&tmem_full[b]);
+            umma_commit_e(&empty[s]);
+            if (kc == Cfg::kKC - 1) umma_commit_e(&tmem_full[b]);
           }
           __syncwarp();
         }
       }
       // last item of this atom tile: the z tile may be overwritten once these MMAs are done
-      if ((item + 1 == item_hi || (item + 1) / n_chunks != tile) && lane == 0) umma_commit(a_free);
+      if ((item + 1 == item_hi || (item + 1) / n_chunks != tile)) umma_commit_e(a_free);
       __syncwarp();
     }
   }

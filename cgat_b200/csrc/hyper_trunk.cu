@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(kTThreads, 1) hyper_trunk_kernel(const TrunkAr
           const uint32_t sg = cnt % kTStages, u = cnt / kTStages;
           mbar_wait(&full[sg], u & 1u);
           tc_fence_after();
-          if (lane == 0) {
+          {  // all lanes, warp-uniform operands; one elected lane issues (tc_common.cuh "_e" forms)
             const uint32_t a_hi = smem_u32(a_smem + kc * kPackStageBytes), a_lo = a_hi + kPackImageBytes;
             const uint32_t b_hi = smem_u32(b_smem + sg * kPackStageBytes), b_lo = b_hi + kPackImageBytes;
             // The tensor core truncates (rounds toward zero) the fp32 accumulator on every accumulating MMA, a
@@ -235,19 +235,19 @@ __global__ void __launch_bounds__(kTThreads, 1) hyper_trunk_kernel(const TrunkAr
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
-              umma_tf32(d_corr, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-              umma_tf32(d_corr, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
+              umma_tf32_e(d_corr, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              umma_tf32_e(d_corr, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
             }
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t off = ks * 32;
-              umma_tf32(d_main, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc,
+              umma_tf32_e(d_main, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc,
                         (kc == kTKC - 1) ? 1u : (uint32_t)(ks != 0));
             }
-            umma_commit(&empty[sg]);
+            umma_commit_e(&empty[sg]);
             if (kc == kTKC - 1) {
-              umma_commit(acc_full);
-              if (s == kTSteps - 1) umma_commit(a_free);
+              umma_commit_e(acc_full);
+              if (s == kTSteps - 1) umma_commit_e(a_free);
             }
           }
           __syncwarp();
