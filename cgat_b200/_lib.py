@@ -19,7 +19,7 @@ _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
 
-ABI_VERSION = 5  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
+ABI_VERSION = 6  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
 
 # name -> (restype, argtypes); must list every symbol declared in include/cgat_b200.h
 SIGNATURES = {
@@ -56,6 +56,7 @@ SIGNATURES = {
     "cgat_hyper_trunk_bwd": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P]),
     "cgat_gemm3x_tn_batched": (ctypes.c_int, [_P, _P, _I32, _I64, _I64, _P, _P, _I64, _I64, _I64, _I32, _P]),
     "cgat_hyper_rowscale_parts": (_I32, [_I64, _I32]),
+    "cgat_hyper_rowscale_parts_f16": (_I32, [_I64, _I32]),
     "cgat_hyper_rowscale": (ctypes.c_int, [_P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_rowscale_f16_amax": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),
     "cgat_hyper_wgrad_f16": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _I64, _I32, _P]),

@@ -1,6 +1,6 @@
 """In-tree nvcc build of libcgat_b200.so for sm_100a (no torch headers involved: plain C ABI).
 
-    python -m cgat_b200.build [--force] [--trap-barriers]
+    python -m cgat_b200.build [--force] [--trap-barriers] [--variant NAME -DMACRO[=V] ...]
 
 Every .cu under csrc/ is compiled to an object file (in parallel, cached by a digest of the source, the
 headers and the flags) and linked into one shared library next to this file.  `--trap-barriers` builds
@@ -66,10 +66,13 @@ def _compile_one(src, flags, hdig, tag, verbose):
     return obj, log, True
 
 
-def build(force=False, verbose=False, trap=False):
-    """Compile every .cu under csrc/ into one shared library. Returns the library path."""
-    flags = NVCC_FLAGS + (TRAP_FLAGS if trap else [])
+def build(force=False, verbose=False, trap=False, variant=None, defines=()):
+    """Compile every .cu under csrc/ into one shared library. Returns the library path.
+    `variant` + `defines` build libcgat_b200_<variant>.so with extra -D flags (experiments; CGAT_B200_LIB=<variant>)."""
+    flags = NVCC_FLAGS + (TRAP_FLAGS if trap else []) + [f"-D{d}" for d in defines]
     lib, tag = (LIB_TRAP, "_trap") if trap else (LIB, "")
+    if variant:
+        lib, tag = os.path.join(ROOT, f"libcgat_b200_{variant}.so"), f"_{variant}"
     os.makedirs(OBJ, exist_ok=True)
     if force:
         for f in glob.glob(os.path.join(OBJ, f"*{tag}.o.stamp")):
@@ -85,7 +88,7 @@ def build(force=False, verbose=False, trap=False):
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError(f"linking {os.path.basename(lib)} failed")
-    if not trap:
+    if not trap and not variant:
         # ptxas resource usage of the objects rebuilt in this call (registers / spills per kernel)
         with open(os.path.join(ROOT, "build_ptxas.log"), "a" if not force else "w") as fh:
             fh.write("".join(r[1] for r in results))
@@ -93,4 +96,7 @@ def build(force=False, verbose=False, trap=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trap="--trap-barriers" in sys.argv))
+    _variant = sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None
+    _defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv, trap="--trap-barriers" in sys.argv,
+                variant=_variant, defines=_defs))

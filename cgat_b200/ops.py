@@ -385,7 +385,7 @@ class _HyperLinear(torch.autograd.Function):
         n, f = y.shape
         ff = f * f
         g = _f32c(g)
-        parts = int(_lib.load().cgat_hyper_rowscale_parts(n, f))
+        parts = int(_lib.load().cgat_hyper_rowscale_parts_f16(n, f) if ctx.f16 else _lib.load().cgat_hyper_rowscale_parts(n, f))
         rowscale = "cgat_hyper_rowscale_f16" if ctx.f16 else "cgat_hyper_rowscale"
         work = dict(key="hyper_rowscale", bound="tensor", flops=2.0 * n * f * ff,
                     note="f16x3: 3 kind::f16 passes per algorithmic flop" if ctx.f16 else

@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CGAT_B200_ABI_VERSION 5 /* 2: bwd_prep bias_sums; f16 entry points. 3: train-step glue. 4: dz_amax. 5: n_ranks, status flags */
+#define CGAT_B200_ABI_VERSION 6 /* 2: bwd_prep bias_sums; f16 entry points. 3: train-step glue. 4: dz_amax. 5: n_ranks, status flags. 6: parts_f16 */
 
 int cgat_abi_version(void);
 const char* cgat_last_error(void);
@@ -195,6 +195,9 @@ int cgat_hyper_rowdot_fwd_f16(const float* z, const float* y_in, const float* e_
                               void* stream);
 int cgat_hyper_rowscale_f16(const float* a, const float* scale, const float* w_bias, const float* w_packed,
                             float* partial, int64_t n_atoms, int32_t f, void* stream);
+/* Partial slots of the f16 form (its own work split: when there are enough SMs it gives every atom tile a fixed
+ * number of CTAs, each with a slice of the output channels): partial holds this many x n_atoms x f floats.     */
+int32_t cgat_hyper_rowscale_parts_f16(int64_t n_atoms, int32_t f);
 
 /* Weight gradient of the hyper-linear layer: dL/dW[o*F+i, k] = sum_n g[n,o] y[n,i] z[n,k], contracted over
  * atoms with MN-major operands; the scaled rows g[n,o]*y[n,:] are formed while staging (the reference's
