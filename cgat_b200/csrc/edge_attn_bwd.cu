@@ -783,6 +783,12 @@ extern "C" int cgat_edge_attn_dgrad(const float* d_gate, const float* d_msg, con
 
 // kind::f16 form of the d_pre variant (identity edge order): wt_*_packed = cgat_pack_kmajor_f16 of W2^T per head,
 // dz_amax = the device float cgat_edge_attn_bwd_prep left (max |d_gate|, |d_msg|).  Writes d_pre (E, 2*H*Hd).
+// F = 128: the rebuilt d_pre kernel of edge_dgrad_f16.cu (dZ tile converted once for all hidden halves)
+int cgat_edge_dgrad_zr_launch(const float* d_gate, const float* d_msg, const uint32_t* signs, const int32_t* segptr,
+                              const float* wt_a_packed, const float* wt_m_packed, const float* dz_amax, float* d_pre,
+                              int64_t n_atoms, int64_t n_edges, int32_t heads, int32_t hd, int32_t grid,
+                              cudaStream_t stream);
+
 extern "C" int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg, const uint32_t* signs,
                                         const int32_t* segptr, const int32_t* seg, const float* wt_a_packed,
                                         const float* wt_m_packed, const float* dz_amax, float* d_pre, int64_t n_atoms,
@@ -794,6 +800,9 @@ extern "C" int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg,
                     "with ceil(hd / 128) * 128 rows per head)");
   if (!d_pre || !dz_amax) return fail(-2, "cgat_edge_attn_dgrad_f16: d_pre and dz_amax are required");
   if (n_atoms <= 0 || n_edges <= 0) return 0;
+  if (f == kBF)
+    return cgat_edge_dgrad_zr_launch(d_gate, d_msg, signs, segptr, wt_a_packed, wt_m_packed, dz_amax, d_pre, n_atoms,
+                                     n_edges, heads, hd, cgat_edge_attn_dgrad_grid(n_edges), stream);
   static bool configured = false;
   if (!configured) {
     CGAT_CUDA(cudaFuncSetAttribute(edge_dgrad_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kBSmemBytes));

@@ -9,10 +9,14 @@
 // CGAT/Hypernetworksmp.py:36-83) and their transposes in backward.
 //
 // Structure (one 128 x BN output tile per CTA):
-//   warps 0-3  producers: global -> registers (float4, coalesced) -> hi/lo split -> shared memory in
-//              the canonical K-major SWIZZLE_128B UMMA layout; then the epilogue (tcgen05.ld ->
-//              bias/activation -> global)
-//   warp  4    allocates TMEM and issues the MMAs from one thread; tcgen05.commit releases stages
+//   warps 0-7  producers in two groups of 128 that take alternate K chunks: global -> registers (float4,
+//              coalesced) -> hi/lo split -> shared memory in the canonical K-major SWIZZLE_128B UMMA layout.
+//              Every group keeps the loads of its NEXT chunk in flight while it converts and stores the
+//              current one (round 1 loaded A, waited, loaded B, waited, once per chunk with 128 threads:
+//              two exposed HBM round trips per chunk, 3 us per 32-float chunk in the in-graph profile
+//              profiles/r03m — 40 TFLOP/s).  Then the epilogue (tcgen05.ld -> bias/activation -> global),
+//              the column blocks dealt to the two groups.
+//   warp  8    allocates TMEM and issues the MMAs; tcgen05.commit releases stages
 //   kStages-deep ring of (A_hi, A_lo, B_hi, B_lo) K-chunks of 32 floats, full/empty mbarriers.
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -24,7 +28,9 @@ using namespace tc;
 
 constexpr int kBM = 128;       // rows of the output tile = TMEM lanes
 constexpr int kKC = 32;        // K floats per chunk = one 128-byte swizzle row
-constexpr int kWorkers = 128;  // producer / epilogue threads
+constexpr int kGroup = 128;    // threads of one producer group (= the 128 TMEM lanes in the epilogue)
+constexpr int kWorkers = 2 * kGroup;  // producer / epilogue threads
+constexpr int kMmaWarp = kWorkers / 32;
 constexpr int kThreads = kWorkers + 32;
 
 template <int BN>
@@ -45,24 +51,25 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   }
 }
 
-// stage a [rows x 32] fp32 chunk (row-major source with leading dimension ld) as hi/lo SW128 tiles
+// a [rows x 32] fp32 chunk (row-major source with leading dimension ld): loads into registers ...
 template <int ROWS>
-__device__ __forceinline__ void stage_chunk(const float* __restrict__ src, int64_t ld, int row0, int n_rows,
-                                            int k0, int k_total, uint8_t* hi, uint8_t* lo, int tid) {
-  constexpr int kIters = ROWS * 8 / kWorkers;
-  float4 v[kIters];
+__device__ __forceinline__ void load_chunk(const float* __restrict__ src, int64_t ld, int row0, int n_rows, int k0,
+                                           int k_total, float4 (&v)[ROWS * 8 / kGroup], int t) {
 #pragma unroll
-  for (int j = 0; j < kIters; ++j) {
-    int idx = tid + kWorkers * j;
-    int r = idx >> 3, c = idx & 7;
-    int gr = row0 + r, gk = k0 + c * 4;
+  for (int j = 0; j < ROWS * 8 / kGroup; ++j) {
+    const int idx = t + kGroup * j, r = idx >> 3, c = idx & 7;
+    const int gr = row0 + r, gk = k0 + c * 4;
     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gr < n_rows && gk < k_total) v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)gr * ld + gk));
   }
+}
+// ... and from there as hi/lo SW128 tiles into a stage
+template <int ROWS>
+__device__ __forceinline__ void store_chunk(const float4 (&v)[ROWS * 8 / kGroup], uint8_t* hi, uint8_t* lo, int t) {
 #pragma unroll
-  for (int j = 0; j < kIters; ++j) {
-    int idx = tid + kWorkers * j;
-    uint32_t off = sw128_offset(idx >> 3, idx & 7);
+  for (int j = 0; j < ROWS * 8 / kGroup; ++j) {
+    const int idx = t + kGroup * j;
+    const uint32_t off = sw128_offset(idx >> 3, idx & 7);
     float4 h, l;
     split_tf32(v[j], h, l);
     *reinterpret_cast<float4*>(hi + off) = h;
@@ -98,7 +105,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 
   if (tid == 0) {
     for (int s = 0; s < S::kStages; ++s) {
-      mbar_init(&full[s], kWorkers);
+      mbar_init(&full[s], kGroup);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum, 1);
@@ -106,33 +113,50 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
   }
   // columns [0,BN): hi*hi sum; [BN,2BN): the 2^-11-sized correction terms, kept apart so the large
   // accumulator is truncated K/8 times instead of 3K/8 (the tensor core truncates on every MMA)
-  if (warp == 4) tmem_alloc(tmem_slot, 2 * BN);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 2 * BN);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kMmaWarp) {
     // ---------------- producers ----------------
-    for (int kc = 0; kc < nk; ++kc) {
+    const int grp = warp >> 2, t = tid & (kGroup - 1);
+    float4 a0[kBM * 8 / kGroup], b0[BN * 8 / kGroup], a1[kBM * 8 / kGroup], b1[BN * 8 / kGroup];
+    auto fetch = [&](float4 (&a)[kBM * 8 / kGroup], float4 (&b)[BN * 8 / kGroup], int kc) {
+      load_chunk<kBM>(A, lda, m0, M, k_begin + kc * kKC, k_end, a, t);
+      load_chunk<BN>(B, ldb, n0, N, k_begin + kc * kKC, k_end, b, t);
+    };
+    auto put = [&](const float4 (&a)[kBM * 8 / kGroup], const float4 (&b)[BN * 8 / kGroup], int kc) {
       const int s = kc % S::kStages, u = kc / S::kStages;
       mbar_wait(&empty[s], (u + 1) & 1);  // passes immediately on the first use of a stage
       uint8_t* st = smem + s * S::kStageBytes;
-      stage_chunk<kBM>(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + S::kABytes, tid);
-      stage_chunk<BN>(B, ldb, n0, N, k_begin + kc * kKC, k_end, st + 2 * S::kABytes, st + 2 * S::kABytes + S::kBBytes, tid);
+      store_chunk<kBM>(a, st, st + S::kABytes, t);
+      store_chunk<BN>(b, st + 2 * S::kABytes, st + 2 * S::kABytes + S::kBBytes, t);
       fence_async_smem();
       mbar_arrive(&full[s]);
+    };
+    int kc = grp;
+    if (kc < nk) fetch(a0, b0, kc);
+    while (kc < nk) {
+      if (kc + 2 < nk) fetch(a1, b1, kc + 2);
+      put(a0, b0, kc);
+      kc += 2;
+      if (kc >= nk) break;
+      if (kc + 2 < nk) fetch(a0, b0, kc + 2);
+      put(a1, b1, kc);
+      kc += 2;
     }
     // ---------------- epilogue ----------------
     mbar_wait(accum, 0);
     tc_fence_after();
-    const int m = m0 + warp * 32 + lane;
+    const int m = m0 + (warp & 3) * 32 + lane;
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
+    for (int cc = grp; cc < BN / 32; cc += 2) {
       float v[32], w[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + BN + cc * 32, w);
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + BN + cc * 32, w);
       tmem_ld_wait();
       const int nb = n0 + cc * 32;
       if (m < M) {
@@ -182,7 +206,7 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
     if (nk == 0 && lane == 0) mbar_arrive(accum);  // empty split: nothing to wait for
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 2 * BN);
   }
@@ -195,22 +219,25 @@ gemm3x_nt_kernel(const float* __restrict__ A, int64_t lda, const float* __restri
 // One 128 x 128 tile per CTA; split-K over blockIdx.z writes partial tiles that the caller sums.
 constexpr int kTnImage = 32 * 128;  // 32 K-rows x 128 B
 
-template <bool kSum>
-__device__ __forceinline__ void stage_chunk_mn(const float* __restrict__ src, int64_t ld, int col0, int n_cols,
-                                               int k0, int k_end, uint8_t* hi, uint8_t* lo, int tid, float4& csum) {
-  float4 v[8];
+// a [32 K-rows x 128 columns] fp32 chunk of an MN-major operand: loads into registers ...
+__device__ __forceinline__ void load_chunk_mn(const float* __restrict__ src, int64_t ld, int col0, int n_cols, int k0,
+                                              int k_end, float4 (&v)[8], int t) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int idx = tid + kWorkers * j, r = idx >> 5, q = idx & 31;
+    const int idx = t + kGroup * j, r = idx >> 5, q = idx & 31;
     const int gk = k0 + r, gc = col0 + q * 4;
     v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (gk < k_end && gc < n_cols) v[j] = __ldg(reinterpret_cast<const float4*>(src + (int64_t)gk * ld + gc));
-    if (kSum) csum.x += v[j].x, csum.y += v[j].y, csum.z += v[j].z, csum.w += v[j].w;  // q is fixed per thread
   }
+}
+// ... and from there as hi/lo MN-major SW128 images into a stage (kSum: column sums on the way, q is fixed per thread)
+template <bool kSum>
+__device__ __forceinline__ void store_chunk_mn(const float4 (&v)[8], uint8_t* hi, uint8_t* lo, int t, float4& csum) {
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int idx = tid + kWorkers * j, r = idx >> 5, q = idx & 31;
+    const int idx = t + kGroup * j, r = idx >> 5, q = idx & 31;
     const uint32_t off = (q >> 3) * kTnImage + mn_sw128_offset(r, q & 7);
+    if (kSum) csum.x += v[j].x, csum.y += v[j].y, csum.z += v[j].z, csum.w += v[j].w;
     float4 h, l;
     split_tf32(v[j], h, l);
     *reinterpret_cast<float4*>(hi + off) = h;
@@ -251,52 +278,71 @@ gemm3x_tn_kernel(const TnArgs g) {
   const int nk = k_end > k_begin ? (k_end - k_begin + kKC - 1) / kKC : 0;  // empty split: zeros, see gemm3x_nt_kernel
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full[s], kWorkers);
+      mbar_init(&full[s], kGroup);
       mbar_init(&empty[s], 1);
     }
     mbar_init(accum, 1);
     mbar_init_fence();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 256);
+  if (warp == kMmaWarp) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  if (warp < 4) {
+  if (warp < kMmaWarp) {
     const bool do_sum = g.colsum != nullptr && blockIdx.x == 0;
+    const int grp = warp >> 2, t = tid & (kGroup - 1);
     float4 csum = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int kc = 0; kc < nk; ++kc) {
+    // two groups on alternate chunks, the next chunk's loads in flight while the current one is converted (see the
+    // file comment)
+    float4 a0[8], b0[8], a1[8], b1[8];
+    auto fetch = [&](float4 (&a)[8], float4 (&b)[8], int kc) {
+      load_chunk_mn(A, lda, m0, M, k_begin + kc * kKC, k_end, a, t);
+      load_chunk_mn(B, ldb, n0, N, k_begin + kc * kKC, k_end, b, t);
+    };
+    auto put = [&](const float4 (&a)[8], const float4 (&b)[8], int kc) {
       const int s = kc % kStages, u = kc / kStages;
       mbar_wait(&empty[s], (u + 1) & 1);
       uint8_t* st = smem + s * kStageBytes;
-      if (do_sum) stage_chunk_mn<true>(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + kOp, tid, csum);
-      else stage_chunk_mn<false>(A, lda, m0, M, k_begin + kc * kKC, k_end, st, st + kOp, tid, csum);
-      stage_chunk_mn<false>(B, ldb, n0, N, k_begin + kc * kKC, k_end, st + 2 * kOp, st + 3 * kOp, tid, csum);
+      if (do_sum) store_chunk_mn<true>(a, st, st + kOp, t, csum);
+      else store_chunk_mn<false>(a, st, st + kOp, t, csum);
+      store_chunk_mn<false>(b, st + 2 * kOp, st + 3 * kOp, t, csum);
       fence_async_smem();
       mbar_arrive(&full[s]);
+    };
+    int kc = grp;
+    if (kc < nk) fetch(a0, b0, kc);
+    while (kc < nk) {
+      if (kc + 2 < nk) fetch(a1, b1, kc + 2);
+      put(a0, b0, kc);
+      kc += 2;
+      if (kc >= nk) break;
+      if (kc + 2 < nk) fetch(a0, b0, kc + 2);
+      put(a1, b1, kc);
+      kc += 2;
     }
     mbar_wait(accum, 0);
     tc_fence_after();
     if (do_sum) {
-      // column sums of A over this split's rows (bias gradients): lane = column group, the 4 warps hold
+      // column sums of A over this split's rows (bias gradients): lane = column group, the 8 warps hold
       // disjoint row sets; the operand stages are free again once `accum` has fired
       float4* red = reinterpret_cast<float4*>(smem);
       red[tid] = csum;
       asm volatile("bar.sync 1, %0;" ::"n"(kWorkers) : "memory");
       const float* rf = reinterpret_cast<const float*>(smem);
-      const int q = tid >> 2, comp = tid & 3;
-      float t = 0.f;
+      const int q = (tid & 127) >> 2, comp = tid & 3;
+      float sum = 0.f;
 #pragma unroll
-      for (int w = 0; w < 4; ++w) t += rf[(w * 32 + q) * 4 + comp];
-      if (m0 + tid < M) g.colsum[((int64_t)split * g.batch + entry) * M + m0 + tid] = t;
+      for (int w = 0; w < 8; ++w) sum += rf[(w * 32 + q) * 4 + comp];
+      if (tid < 128 && m0 + tid < M) g.colsum[((int64_t)split * g.batch + entry) * M + m0 + tid] = sum;
     }
-    const int m = m0 + warp * 32 + lane;
+    const int m = m0 + (warp & 3) * 32 + lane;
     float* cbase = g.c + (int64_t)split * g.split_stride + (int64_t)entry * g.batch_stride;
 #pragma unroll 1
-    for (int cc = 0; cc < 4; ++cc) {
+    for (int cc = grp; cc < 4; cc += 2) {
       float v[32], w[32];
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + cc * 32, v);
-      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 128 + cc * 32, w);
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + cc * 32, v);
+      tmem_ld32(tmem + ((uint32_t)((warp & 3) * 32) << 16) + 128 + cc * 32, w);
       tmem_ld_wait();
       if (m < M) {
         float* crow = cbase + (int64_t)m * ldc + n0 + cc * 32;
@@ -332,7 +378,7 @@ gemm3x_tn_kernel(const TnArgs g) {
     if (nk == 0 && lane == 0) mbar_arrive(accum);
   }
   __syncthreads();
-  if (warp == 4) {
+  if (warp == kMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
