@@ -30,6 +30,9 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#ifndef CGAT_EFWD_DBG
+#define CGAT_EFWD_DBG 0   // timing experiments: 1 no MMAs, 2 no gathers / conversion, 4 no W2 stream, 8 no epilogue math
+#endif
 namespace cgat {
 namespace {
 using namespace tc;
@@ -228,7 +231,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             }
           }
 #pragma unroll 1
-          for (int cc = 0; cc < kET / 16; ++cc) {
+          for (int cc = 0; cc < ((CGAT_EFWD_DBG & 8) ? 0 : kET / 16); ++cc) {
             float av[16], vv[16];
             tmem_ld16(tbase + cc * 16, av);
             tmem_ld16(tbase + 128 + cc * 16, vv);
@@ -276,7 +279,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           float* pm = g.d_msg + (int64_t)e0 * hf + hc;
           float sum_m = 0.f, sum_g = 0.f;  // this tile's column sums of d_msg / d_gate for (head h, channel c)
 #pragma unroll 1
-          for (int cc = 0; cc < kET / 8; ++cc) {
+          for (int cc = 0; cc < ((CGAT_EFWD_DBG & 8) ? 0 : kET / 8); ++cc) {
             // per-segment statistics re-read per column: same address for the ~max_nbr edges of a segment, so these
             // are L1 hits; it keeps the column code free of branches.  8 columns per batch: 32 loads in flight and
             // everything stays in registers under the 80-register cap of an 800-thread CTA
@@ -360,7 +363,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             const uint32_t s = cnt % kEStages, u = cnt / kEStages;
             mbar_wait(&empty[s], (u + 1) & 1u);
             uint8_t* st = stages + s * kEStageBytes;
-            if (pl == 0) {
+            if (pl == 0 && !(CGAT_EFWD_DBG & 4)) {
               mbar_expect_tx(&full[s], kPackStageBytes);
               bulk_g2s(st, w2[net] + ((int64_t)h * kcn + kc) * kPackStageBytes, kPackStageBytes, &full[s]);
             }
@@ -370,7 +373,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               uint8_t* bh = st + kPackStageBytes;
               const int col0 = (h / vh) * hd + kc * kPackChunk16;
 #pragma unroll 1
-              for (int j0 = 0; j0 < 4; j0 += 2) {
+              for (int j0 = 0; j0 < ((CGAT_EFWD_DBG & 2) ? 0 : 4); j0 += 2) {
                 float4 pd[2][2], ps[2][2], te[2][2];
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
@@ -495,7 +498,8 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) {
                 const uint32_t off = ks * 32;
-                if constexpr (kF16) {  // K = 16 halves = the same 32 bytes of the swizzled row
+                if constexpr (kF16 && (CGAT_EFWD_DBG & 1)) {
+                } else if constexpr (kF16) {  // K = 16 halves = the same 32 bytes of the swizzled row
                   umma_f16_e(d, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
                   umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
                   umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
