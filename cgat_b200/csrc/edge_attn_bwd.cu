@@ -644,11 +644,17 @@ struct ReduceArgs {
 
 __global__ void __launch_bounds__(kSRThreads) edge_reduce_kernel(const ReduceArgs g) {
   extern __shared__ float4 sr_acc[];  // [n_ranks][kSRThreads]
-  const ReducePass& ps = g.pass[blockIdx.z];
+  // pass = lowest bit of blockIdx.y: the by-destination and the by-source CTA of one atom chunk are scheduled side by
+  // side, and the out-edges of an atom end in its own crystal, i.e. in rows the neighbour CTA reads at about the same
+  // time — part of the second read of d_pre (683 MB at the bench size, five times the L2) is then served by L2
+  // (365 -> 330 us).  Measured and dropped: one CTA per chunk that stages the chunk's rows in shared memory once and
+  // takes both sums from there — with 64- or 32-column blocks (all that fits next to the rows of 20-40 atoms) the
+  // 128-256-byte row pieces cost more in DRAM efficiency than the second read saves (540-615 us).
+  const ReducePass& ps = g.pass[blockIdx.y & 1u];
   const int tid = threadIdx.x;
   const int col = blockIdx.x * kSRCols + tid * 4;
   const bool active = col < g.cols;
-  const int chunk = blockIdx.y;
+  const int chunk = blockIdx.y >> 1;
   const int a_lo = (int)((int64_t)g.n_atoms * chunk / g.n_chunks);
   const int a_hi = (int)((int64_t)g.n_atoms * (chunk + 1) / g.n_chunks);
   const bool ranks = ps.rnk != nullptr && ps.d_rank != nullptr;
@@ -741,7 +747,7 @@ extern "C" int cgat_edge_attn_reduce(const float* d_pre, int64_t ldd, const int3
                                    kBMaxRanks * kSRThreads * (int)sizeof(float4)));
     configured = true;
   }
-  dim3 grid((unsigned)ceil_div(cols, kSRCols), (unsigned)n_chunks, 2);
+  dim3 grid((unsigned)ceil_div(cols, kSRCols), (unsigned)(2 * n_chunks), 1);
   edge_reduce_kernel<<<grid, kSRThreads, smem, stream>>>(a);
   return check_launch("edge_reduce_kernel");
 }
