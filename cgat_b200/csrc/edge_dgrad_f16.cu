@@ -14,6 +14,10 @@
 //     hidden layer (Hd = 256: twice).  Here the converted tile stays in shared memory for all halves: the ring is split
 //     into a W2 ring (3 x 32 KB, copy engine) and two whole-K dZ buffers (2 x 64 KB).
 //   * the producers looked up segment metadata nobody reads in this form and met at a 256-thread barrier per tile.
+// Measured and dropped: taking the per-destination segment sums of d_pre in this epilogue (thread = hidden unit, running
+// sum over the destination-sorted columns, a store at every segment end) so that cgat_edge_attn_reduce only makes its
+// by-source pass — the reduce went from 330 to 208 us but this kernel from 260 to 417 us (one warp-uniform branch per
+// column splits the unrolled column loop into basic blocks and the epilogue is what the kernel waits for).
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -254,7 +258,7 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- MMA issuer (all lanes, one elected lane issues)
-    constexpr uint32_t idesc = umma_idesc_f16(128, kT);
+    constexpr uint32_t idesc = umma_idesc_f16(128, kT), idesc2 = umma_idesc_f16(128, 2 * kT);
     uint32_t wc = 0, step = 0;
     for (int zc = 0; zc < n_z; ++zc) {
       const uint32_t zb = (uint32_t)zc & 1u;
@@ -276,9 +280,11 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
           for (int ks = 0; ks < 4; ++ks) {
             const uint32_t off = ks * 32;
             if (!(CGAT_EDGE_DBG & 2)) {
-              umma_f16_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
-              umma_f16_e(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc, 1);
-              umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc, (kc | ks) != 0);
+              // the hi and lo images of the dZ chunk are adjacent: one N = 256 MMA multiplies W_hi with both (main |
+              // correction columns), one N = 128 MMA adds W_lo * dZ_hi to the correction columns
+              (void)b_lo;
+              umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+              umma_f16_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
             }
           }
           umma_commit_e(&w_empty[s]);

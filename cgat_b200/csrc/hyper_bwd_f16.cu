@@ -13,6 +13,9 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#ifndef CGAT_HW_DBG
+#define CGAT_HW_DBG 0   // timing experiments (F = 128 kernel): 1 no MMAs, 2 no operand conversion / stores, 4 no loads either, 8 no tail sums
+#endif
 namespace cgat {
 namespace {
 using namespace tc;
@@ -113,7 +116,7 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
         const int n = n0 + r;
         zv[j] = yv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         g0[j] = g1[j] = 0.f;
-        if (n < n_hi) {
+        if (n < n_hi && !(CGAT_HW_DBG & 4)) {
           zv[j] = __ldg(reinterpret_cast<const float4*>(z + (int64_t)n * kF) + q);
           yv[j] = __ldg(reinterpret_cast<const float4*>(y + (int64_t)n * kF) + q);
           const float2 gg = __ldg(reinterpret_cast<const float2*>(g + (int64_t)n * kF + o0));
@@ -123,7 +126,7 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
       mbar_wait(&empty[st], (u + 1) & 1u);
       uint8_t* sb = smem + st * kStage;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < ((CGAT_HW_DBG & 2) ? 0 : 4); ++j) {
         const int idx = pl + 256 * j, r = idx >> 5, q = idx & 31;
         const uint32_t off = (q >> 4) * kImg + mn16_offset(r, q & 15);
         uint2 hi, lo;
@@ -162,7 +165,7 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
       tail[((int64_t)split * kF + o0 + (kind & 1)) * 2 * kF + (kind >> 1) * kF + col] = acc * s_inv;
     }
   } else {
-    constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128);
+    constexpr uint32_t idesc = umma_idesc_f16_mn(128, 128), idesc2 = umma_idesc_f16_mn(128, 256);
     for (int ch = 0; ch < n_chunks; ++ch) {
       const int st = ch % kStagesW, u = ch / kStagesW;
       mbar_wait(&full[st], u & 1u);
@@ -176,11 +179,15 @@ hyper_wgrad_f16_kernel(const float* __restrict__ g, const float* __restrict__ y,
 #pragma unroll
           for (int ks = 0; ks < kRows / 16; ++ks) {   // one MMA consumes 16 K-rows = two 1024-byte groups of every image
             const uint32_t o = ks * 2048;
-            umma_f16_e(d + 128, umma_desc_mn_sw128_16b(a_lo + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
+            if (CGAT_HW_DBG & 1) continue;
+            // the hi and lo images of z are adjacent (4 images of 64 columns): ONE N = 256 MMA multiplies a_hi with both
+            // and writes main | correction columns, a second N = 128 MMA adds a_lo * z_hi to the correction columns —
+            // 20 KB of shared-memory operand reads per K step instead of 24 (the kernel runs at the shared-memory port:
+            // operand reads + the producers' stores, profiles/r03z)
+            (void)z_lo;
+            umma_f16_e(d, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc2,
                      (ch | ks) != 0);
-            umma_f16_e(d + 128, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_lo + o, kImg), idesc, 1);
-            umma_f16_e(d, umma_desc_mn_sw128_16b(a_hi + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc,
-                     (ch | ks) != 0);
+            umma_f16_e(d + 128, umma_desc_mn_sw128_16b(a_lo + o, kImg), umma_desc_mn_sw128_16b(z_hi + o, kImg), idesc, 1);
           }
         }
         umma_commit_e(&empty[st]);

@@ -33,3 +33,10 @@ ms = t(lambda: _lib.call("cgat_hyper_rowscale_f16", _lib.ptr(z), _lib.ptr(g), _l
 print(f"[{os.environ.get('CGAT_B200_LIB','')}] rowscale n={n} f={f}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s")
 ms = t(lambda: _lib.call("cgat_hyper_rowdot_fwd_f16", _lib.ptr(z), _lib.ptr(y), _lib.ptr(e), None, _lib.ptr(bias), _lib.ptr(wp), _lib.ptr(out), n, f, _lib.stream()))
 print(f"[{os.environ.get('CGAT_B200_LIB','')}] rowdot   n={n} f={f}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s")
+
+splits = int(lib.cgat_hyper_wgrad_splits(n)) if hasattr(lib, "cgat_hyper_wgrad_splits") else 2
+gam = g.abs().max().reshape(1).contiguous()
+wout = torch.empty((splits, f * f, f), device=dev)
+tail = torch.empty((splits, f, 2 * f), device=dev)
+ms = t(lambda: _lib.call("cgat_hyper_wgrad_f16", _lib.ptr(g), _lib.ptr(y), _lib.ptr(z), _lib.ptr(gam), _lib.ptr(wout), _lib.ptr(tail), n, f, _lib.stream()))
+print(f"[{os.environ.get('CGAT_B200_LIB','')}] wgrad    n={n} f={f}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s  ({splits} splits)")
