@@ -18,10 +18,10 @@
 //     d4 = (dE We + dZ) * (1 - z^2),  d3 = (d4 W4) * (1 - t3^2),  ...,  d1 = (d2 W2) * (1 - t1^2),  dh_j = d1 W1
 // The pre-activation gradients d_i are stored for the weight gradients (cgat_gemm3x_tn_batched).
 //
-// Roles (288 threads, one persistent CTA per SM):
-//   warps 0-3  epilogue (thread = atom row): tcgen05.ld -> bias/tanh (or tanh') -> global + next A operand
-//   warps 4-7  stage the chain input tile (h, or dE_j); warp 4 lane 0 also streams the packed weights
-//   warp  8    TMEM allocation + single-thread MMA issue (3xTF32, one accumulator per K chunk, see below)
+// Roles (416 threads, one persistent CTA per SM):
+//   warps 0-7   epilogue (thread = atom row x column half): tcgen05.ld -> bias/tanh (or tanh') -> global + next A operand
+//   warps 8-11  stage the chain input tile (h, or dE_j); warp 8 lane 0 also streams the packed weights
+//   warp  12    TMEM allocation + MMA issue (3xTF32, one accumulator per K chunk, see below)
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -36,7 +36,9 @@ constexpr int kTKC = kTF / kPackChunk;
 constexpr int kTABytes = kTKC * (int)kPackStageBytes;  // 128 KB: activation tile, hi+lo
 constexpr int kTStages = 3;
 constexpr int kTSmemBytes = kTABytes + kTStages * (int)kPackStageBytes + 1024 + 512;
-constexpr int kTThreads = 288;
+constexpr int kTEpiWarps = 8;       // two column halves x four lane quadrants (16 warps: 80-register cap, measured slower)
+constexpr int kTMmaWarp = kTEpiWarps + 4;
+constexpr int kTThreads = (kTMmaWarp + 1) * 32;
 constexpr int64_t kTMatFloats = (int64_t)kTKC * (kPackStageBytes / 4);  // one packed F x F matrix
 
 struct TrunkArgs {
@@ -85,15 +87,19 @@ __global__ void __launch_bounds__(kTThreads, 1) hyper_trunk_kernel(const TrunkAr
     mbar_init(tmem_free, 128);
     mbar_init_fence();
   }
-  if (warp == 8) tmem_alloc(tmem_slot, 4 * kTF);
+  if (warp == kTMmaWarp) tmem_alloc(tmem_slot, 4 * kTF);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp < 4) {
+  if (warp < kTEpiWarps) {
     // ------------------------------------------------------------------ epilogue
-    const int r = warp * 32 + lane;  // row of the tile = TMEM lane
+    // 8 warps: warp -> (lane quadrant qd, column half ch).  A chain step is strictly serial (MMA -> this epilogue ->
+    // next MMA), so the epilogue's latency is the step's: with 4 warps (one per scheduler, 128 columns each) it took
+    // 7 of the 8.7 us of a forward step (in-graph profile profiles/r03m: 87 us for two 5-step chains).
+    const int qd = warp & 3, ch = warp >> 2;
+    const int r = qd * 32 + lane;  // row of the tile = TMEM lane
     uint32_t k = 0;                  // global step counter (phase of acc_full)
     for (int item = item_lo; item < item_hi; ++item) {
       const int tile = item / J, j = item - tile * J;
@@ -117,10 +123,10 @@ __global__ void __launch_bounds__(kTThreads, 1) hyper_trunk_kernel(const TrunkAr
           if (s == 0) add = g.dZ + ((int64_t)j * N + n) * kTF;
         }
 #pragma unroll 1
-        for (int c16 = 0; c16 < kTF / 16; ++c16) {
+        for (int c16 = ch * (kTF / 16 / (kTEpiWarps / 4)); c16 < (ch + 1) * (kTF / 16 / (kTEpiWarps / 4)); ++c16) {
           const int cc = c16 >> 1;  // K chunk of the next step this column group belongs to
           float v0[16], v1[16], v2[16], v3[16];
-          const uint32_t tb = tmem + ((uint32_t)(warp * 32) << 16) + c16 * 16;
+          const uint32_t tb = tmem + ((uint32_t)(qd * 32) << 16) + c16 * 16;
           tmem_ld16(tb, v0);
           tmem_ld16(tb + kTF, v1);
           tmem_ld16(tb + 2 * kTF, v2);
@@ -160,17 +166,17 @@ __global__ void __launch_bounds__(kTThreads, 1) hyper_trunk_kernel(const TrunkAr
           }
         }
         tc_fence_before();
-        if (!last) {
-          fence_async_smem();
-          mbar_arrive(a_ready);
-        } else {
-          mbar_arrive(tmem_free);
+        if (!last) fence_async_smem();
+        asm volatile("bar.sync 1, %0;" ::"n"(kTEpiWarps * 32) : "memory");   // both column halves are done
+        if (ch == 0) {   // the barriers count 128 arrivals (the stagers use a_ready too)
+          if (!last) mbar_arrive(a_ready);
+          else mbar_arrive(tmem_free);
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < kTMmaWarp) {
     // ------------------------------------------------------------------ chain-input stagers + weight TMA
-    const int st = tid - 128;
+    const int st = tid - kTEpiWarps * 32;
     uint32_t it = 0, cnt = 0;
     for (int item = item_lo; item < item_hi; ++item, ++it) {
       const int tile = item / J, j = item - tile * J;
@@ -256,7 +262,7 @@ __global__ void __launch_bounds__(kTThreads, 1) hyper_trunk_kernel(const TrunkAr
     }
   }
   __syncthreads();
-  if (warp == 8) {
+  if (warp == kTMmaWarp) {
     tc_fence_after();
     tmem_dealloc(tmem, 4 * kTF);
   }
