@@ -264,6 +264,27 @@ def plan_split(k, want, granule=32):
     return max(1, -(-k // k_per))
 
 
+N_SMS = 148
+
+
+def best_split(tiles, k, max_split, granule=32, fixed=4.0, per_part=0.25):
+    """Split-K count for `tiles` output tiles and a contraction of length k on one-CTA-per-SM kernels: the CTAs run in
+    ceil(tiles * n / 148) waves of ceil(k / n / granule) chunks each, so the count that asks for the most CTAs is often
+    NOT the fastest (15 splits of 20 tiles = 300 CTAs = a third wave for 4 CTAs; 5 splits of 44 tiles = 1.5 waves).
+    Cost in chunk times: waves * (chunks + fixed per-CTA overhead) + per_part * n for the partial sum; ties -> fewer parts."""
+    best, best_cost = 1, None
+    for n in range(1, max(1, int(max_split)) + 1):
+        n_eff = plan_split(k, n, granule)
+        if n_eff != n:
+            continue
+        k_per = -(-(-(-k // n)) // granule) * granule
+        waves = -(-tiles * n // N_SMS)
+        cost = waves * (k_per // granule + fixed) + per_part * n
+        if best_cost is None or cost < best_cost - 1e-9:
+            best, best_cost = n, cost
+    return best
+
+
 def gemm3x_splitk(a, w, n_split=None):
     """a @ w.T for a long contraction with few output tiles (cgat_gemm3x_nt_splitk): a (M,K), w (N,K)."""
     M, K = a.shape
@@ -272,7 +293,7 @@ def gemm3x_splitk(a, w, n_split=None):
         raise ValueError("gemm3x_splitk needs row-contiguous CUDA operands")
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if n_split is None:
-        n_split = max(1, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
+        n_split = best_split(tiles, K, min((K + 511) // 512, (2 * 148 + tiles - 1) // tiles))
     n_split = plan_split(K, n_split)
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_nt_splitk", a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), part.data_ptr(), N, M * N,
@@ -289,7 +310,7 @@ def gemm3x_tn(a, b, n_split=None):
         raise ValueError("gemm3x_tn needs row-contiguous CUDA operands")
     tiles = ((M + 127) // 128) * ((N + 127) // 128)
     if n_split is None:
-        n_split = max(1, min((K + 255) // 256, (2 * 148 + tiles - 1) // tiles))
+        n_split = best_split(tiles, K, min((K + 255) // 256, (2 * 148 + tiles - 1) // tiles))
     n_split = plan_split(K, n_split)
     part = torch.empty((n_split, M, N), dtype=torch.float32, device=a.device)
     _lib.call("cgat_gemm3x_tn", a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), part.data_ptr(), N, M * N,
@@ -470,7 +491,7 @@ def gemm3x_tn_batched(a_list, b_list, colsum=True):
     batch = len(a_list)
     dev = a_list[0].device
     tiles = batch * ((M + 127) // 128) * ((N + 127) // 128)
-    n_split = plan_split(K, max(1, min((K + 255) // 256, (2 * 148) // tiles)))
+    n_split = plan_split(K, best_split(tiles, K, min((K + 255) // 256, (2 * 148) // tiles)))
     part = torch.empty((n_split, batch, M, N), dtype=torch.float32, device=dev)
     csum = torch.empty((n_split, batch, M), dtype=torch.float32, device=dev) if colsum else None
     _lib.call("cgat_gemm3x_tn_batched", _lib.ptr_array(a_list), _lib.ptr_array(b_list), batch, a_list[0].stride(0),

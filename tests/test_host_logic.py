@@ -193,3 +193,22 @@ def test_split_planner_never_emits_an_empty_split():
         want = max(1, min((k + 255) // 256, (2 * 148) // 16))
         n = plan_split(k, want)
         assert (n - 1) * (-(-(-(-k // n)) // 32) * 32) < k
+
+
+def test_wave_aware_split_choice():
+    """ops.best_split picks the split-K count by waves x chunks on the 148 one-CTA-per-SM kernels: it never asks for more
+    parts than allowed, never produces an empty part, and avoids the wave tails the old "as many CTAs as possible" rule
+    produced (20 tiles x 15 parts = 300 CTAs = a third wave for 4 CTAs; 44 tiles x 5 parts = 1.5 waves)."""
+    from cgat_b200.ops import best_split, plan_split
+    assert best_split(20, 5632, 15) == 7          # first-layer weight gradient at the bench size: one wave of 140
+    assert best_split(44, 2560, 5) == 3           # first-layer input gradient: one wave of 132
+    for tiles in (1, 2, 4, 16, 20, 44, 80, 148, 300):
+        for k in (1, 31, 32, 33, 501, 2560, 5376, 5632, 6400, 66000):
+            for max_split in (1, 2, 5, 15, 22, 74):
+                n = best_split(tiles, k, max_split)
+                assert 1 <= n <= max_split
+                assert plan_split(k, n) == n      # no empty part
+                k_per = -(-(-(-k // n)) // 32) * 32
+                waves = -(-tiles * n // 148)
+                # never worse (in waves x chunks) than not splitting at all
+                assert waves * (k_per // 32 + 4.0) + 0.25 * n <= -(-tiles // 148) * (-(-k // 32) + 4.0) + 0.25 + 1e-9
