@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
             }
           }
 #pragma unroll 1
-          for (int cc = 0; cc < ((CGAT_EFWD_DBG & 8) ? 0 : kET / 16); ++cc) {
+          for (int cc = 0; cc < ((CGAT_EFWD_DBG & 8) ? 0 : (nv + 15) >> 4); ++cc) {   // (the CTA's last tile is partial)
             float av[16], vv[16];
             tmem_ld16(tbase + cc * 16, av);
             tmem_ld16(tbase + 128 + cc * 16, vv);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
           float* pm = g.d_msg + (int64_t)e0 * hf + hc;
           float sum_m = 0.f, sum_g = 0.f;  // this tile's column sums of d_msg / d_gate for (head h, channel c)
 #pragma unroll 1
-          for (int cc = 0; cc < ((CGAT_EFWD_DBG & 8) ? 0 : kET / 8); ++cc) {
+          for (int cc = 0; cc < ((CGAT_EFWD_DBG & 8) ? 0 : (nv + 7) >> 3); ++cc) {   // (the CTA's last tile is partial)
             // per-segment statistics re-read per column: same address for the ~max_nbr edges of a segment, so these
             // are L1 hits; it keeps the column code free of branches.  8 columns per batch: 32 loads in flight and
             // everything stays in registers under the 80-register cap of an 800-thread CTA
@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     for (int tile = 0; tile < n_tiles; ++tile) {
       const int e0 = e_lo + tile * kET;
       const int nv = min(kET, e_hi - e0);
+      const int n16 = (nv + 15) & ~15;
       int32_t* mt = meta + (tile & (kEMetaBufs - 1)) * kEMetaStride;
       if (pt < kET) {
         const bool ok = pt < nv;
@@ -374,6 +375,9 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
               const int col0 = (h / vh) * hd + kc * kPackChunk16;
 #pragma unroll 1
               for (int j0 = 0; j0 < ((CGAT_EFWD_DBG & 2) ? 0 : 4); j0 += 2) {
+                // rows beyond the last 16-column group with edges are not read by this tile's MMAs (N = n16): a group
+                // of 8 lanes shares a row, so the skip is uniform per quarter-warp
+                if (((pl + kEGroup * j0) >> 3) >= n16) break;   // rows grow with j0
                 float4 pd[2][2], ps[2][2], te[2][2];
 #pragma unroll
                 for (int jj = 0; jj < 2; ++jj) {
@@ -479,9 +483,12 @@ __global__ void __launch_bounds__(kEThreads, 1) edge_attn_kernel(const EdgeArgs 
     }
   } else {
     // ---------------------------------------------------------------- MMA issuer
-    constexpr uint32_t idesc = kF16 ? umma_idesc_f16(kEF, kET) : umma_idesc_tf32(kEF, kET);
     uint32_t cnt = 0, hcount = 0;
     for (int tile = 0; tile < n_tiles; ++tile) {
+      // the CTA's last tile is usually partial (E / 148 edges = 3.5 tiles at the bench size): its MMAs cover only the
+      // 16-column groups that hold edges, and the producers / epilogue skip the rest
+      const uint32_t n16 = (uint32_t)((min(kET, e_hi - (e_lo + tile * kET)) + 15) & ~15);
+      const uint32_t idesc = kF16 ? umma_idesc_f16(kEF, n16) : umma_idesc_tf32(kEF, n16);
       for (int h = 0; h < H; ++h, ++hcount) {
         const uint32_t hb = hcount & 1u;
         mbar_wait(&tmem_empty[hb], ((hcount >> 1) + 1) & 1u);

@@ -163,8 +163,8 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
       tmem_ld16(tbase, v[0]);
       tmem_ld16(tbase + 128, w[0]);
 #pragma unroll
-      for (int cc = 0; cc < kT / 16; ++cc) {
-        tmem_ld_wait();
+      for (int cc = 0; cc < kT / 16; ++cc) {   // (stopping at the last column group with edges was measured: the branch
+        tmem_ld_wait();                       //  costs the straight-line schedule more than the partial tile saves)
         if (cc + 1 < kT / 16) {
           tmem_ld16(tbase + (cc + 1) * 16, v[(cc + 1) & 1]);
           tmem_ld16(tbase + 128 + (cc + 1) * 16, w[(cc + 1) & 1]);
@@ -208,10 +208,11 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
         }
       }
     };
-    auto store = [&](uint8_t* bh, const float4* xa, const float4* xb) {
+    auto store = [&](uint8_t* bh, const float4* xa, const float4* xb, int n16) {
 #pragma unroll
       for (int j = 0; j < ((CGAT_EDGE_DBG & 4) ? 0 : 4); ++j) {
         const int idx = pt + kProd * j;
+        if ((idx >> 3) >= n16) break;   // rows beyond the tile's last 16-column group with edges are never read
         const float4 a = make_float4(xa[j].x * s_scale, xa[j].y * s_scale, xa[j].z * s_scale, xa[j].w * s_scale);
         const float4 b = make_float4(xb[j].x * s_scale, xb[j].y * s_scale, xb[j].z * s_scale, xb[j].w * s_scale);
         uint4 hi, lo;
@@ -226,11 +227,13 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
     for (int zc = 0; zc < n_z; ++zc) {
       const uint32_t zb = (uint32_t)zc & 1u;
       uint8_t* zt = zbuf + zb * kZBytes;
+      const int tile_z = zc % n_tiles;
+      const int n16 = (min(kT, e_hi - (e_lo + tile_z * kT)) + 15) & ~15;
       load(zc, 1, a1, b1);
       mbar_wait(&z_empty[zb], (((uint32_t)zc >> 1) + 1) & 1u);   // the MMAs of the tile before last have read the buffer
-      store(zt, a0, b0);
+      store(zt, a0, b0, n16);
       load(zc + 1, 0, a0, b0);
-      store(zt + kPackStageBytes, a1, b1);
+      store(zt + kPackStageBytes, a1, b1, n16);
       fence_async_smem();
       mbar_arrive(&z_full[zb]);
     }
@@ -265,6 +268,8 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
       mbar_wait(&z_full[zb], ((uint32_t)zc >> 1) & 1u);
       tc_fence_after();
       const uint32_t z_base = smem_u32(zbuf + zb * kZBytes);
+      const uint32_t n16 = (uint32_t)((min(kT, e_hi - (e_lo + (zc % n_tiles) * kT)) + 15) & ~15);
+      const uint32_t idesc_p = umma_idesc_f16(128, n16);   // partial (last) tile of the CTA: N = n16 < 128
       for (int half = 0; half < nhalf; ++half, ++step) {
         const uint32_t b = step & 1u;
         mbar_wait(&tmem_empty[b], ((step >> 1) + 1) & 1u);
@@ -282,9 +287,14 @@ __global__ void __launch_bounds__(kThreadsZ, 1) edge_dgrad_zr_kernel(const Dgrad
             if (!(CGAT_EDGE_DBG & 2)) {
               // the hi and lo images of the dZ chunk are adjacent: one N = 256 MMA multiplies W_hi with both (main |
               // correction columns), one N = 128 MMA adds W_lo * dZ_hi to the correction columns
-              (void)b_lo;
-              umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
-              umma_f16_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+              if (n16 == kT) {
+                umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc2, (kc | ks) != 0);
+                umma_f16_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc, 1);
+              } else {   // the lo image does not follow the first n16 rows of the hi image: three N = n16 MMAs
+                umma_f16_e(dc, umma_desc_k_sw128(a_lo + off), umma_desc_k_sw128(b_hi + off), idesc_p, (kc | ks) != 0);
+                umma_f16_e(dc, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_lo + off), idesc_p, 1);
+                umma_f16_e(d, umma_desc_k_sw128(a_hi + off), umma_desc_k_sw128(b_hi + off), idesc_p, (kc | ks) != 0);
+              }
             }
           }
           umma_commit_e(&w_empty[s]);

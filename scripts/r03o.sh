@@ -1,4 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-CGAT_B200_LIB=trap timeout 600 python -m pytest tests/test_gpu_gemm.py -m gpu -q -x 2>&1 | tail -3
-timeout 600 python scripts/profile_graph_step.py cfg2_train 4 2>/dev/null | grep "cfg2_train\|kernels:\|gemm3x\|sum_parts"
+CGAT_B200_LIB=trap timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -q -x -k "edge" 2>&1 | tail -3
+timeout 300 python scripts/edge_time.py 2>&1 | tail -10
+timeout 600 python scripts/profile_graph_step.py cfg2_train 4 2>/dev/null | grep "cfg2_train\|kernels:\|edge_"
