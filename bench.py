@@ -324,10 +324,10 @@ def forward_record(model, rank, world, dev, args, timed):
 KERNEL_NAMES = {  # profile key (ops.py `work`) -> kernel names in the ncu capture (profiles/*_kernel_metrics.json)
     "hyper_rowscale": ["hyper_rowdot_f16_kernel<128, 1>", "hyper_rowdot_fwd_kernel<128, 1>"],
     "hyper_rowdot_fwd": ["hyper_rowdot_f16_kernel<128, 0>", "hyper_rowdot_fwd_kernel<128, 0>"],
-    "hyper_wgrad": "hyper_wgrad_kernel", "hyper_trunk_fwd": "hyper_trunk_kernel<0>",
+    "hyper_wgrad": ["hyper_wgrad_f16_kernel", "hyper_wgrad_kernel"], "hyper_trunk_fwd": "hyper_trunk_kernel<0>",
     "hyper_trunk_bwd": "hyper_trunk_kernel<1>", "edge_attn_fwd": ["edge_attn_kernel<0, 1>", "edge_attn_kernel<0, 0>"],
-    "edge_attn_bwd_prep": ["edge_attn_kernel<1, 1>", "edge_attn_kernel<1, 0>"], "edge_attn_dgrad": "edge_dgrad_kernel",
-    "edge_attn_wgrad": "edge_wgrad_kernel", "edge_attn_reduce": "edge_reduce_kernel",
+    "edge_attn_bwd_prep": ["edge_attn_kernel<1, 1>", "edge_attn_kernel<1, 0>"], "edge_attn_dgrad": ["edge_dgrad_zr_kernel", "edge_dgrad_kernel<1, 1>", "edge_dgrad_kernel"],
+    "edge_attn_wgrad": ["edge_wgrad_f16_kernel", "edge_wgrad_kernel"], "edge_attn_reduce": "edge_reduce_kernel",
     "gemm3x_nt": "gemm3x_nt_kernel<128>", "gemm3x_nt_res": "gemm3x_nt_res_kernel", "gemm3x_tn": "gemm3x_tn_kernel",
     "gemm3x_tn_batched": "gemm3x_tn_kernel",
 }
