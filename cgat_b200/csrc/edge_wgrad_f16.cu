@@ -14,6 +14,9 @@
 #include "common.cuh"
 #include "tc_common.cuh"
 
+#ifndef CGAT_EW_DBG
+#define CGAT_EW_DBG 0   // timing experiments: 1 no MMAs, 2 no hidden-row gathers / conversion, 4 no dZ loads / conversion
+#endif
 namespace cgat {
 namespace {
 using namespace tc;
@@ -135,7 +138,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
       for (int j = 0; j < 4; ++j) {
         const int idx = pl + kWGroup * j, r = idx >> 5, q = idx & 31;
         a[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (r < nv) a[j] = __ldg(reinterpret_cast<const float4*>(dz + ((int64_t)(e0 + r) * H + h) * F + c0 + q * 4));
+        if (r < nv && !(CGAT_EW_DBG & 4)) a[j] = __ldg(reinterpret_cast<const float4*>(dz + ((int64_t)(e0 + r) * H + h) * F + c0 + q * 4));
       }
       float4 x[8];
 #pragma unroll
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
         const int idx = pl + kWGroup * j, r = idx >> 6, q = idx & 63;
         const int d = mt[r];
         x[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (d >= 0 && k0 + q * 4 < hd) {
+        if (d >= 0 && k0 + q * 4 < hd && !(CGAT_EW_DBG & 2)) {
           const int col = net * hhd + h * hd + k0 + q * 4;
           const float4 pd = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)d * ldp + col));
           const float4 ps = __ldg(reinterpret_cast<const float4*>(g.P + (int64_t)mt[32 + r] * ldp + 2 * hhd + col));
@@ -156,7 +159,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
       uint8_t* sb = stages + st * kWStage;
       // A operand: dZ * s (32 edges x 128 channels), images of 64 channels
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < ((CGAT_EW_DBG & 4) ? 0 : 4); ++j) {
         const int idx = pl + kWGroup * j, r = idx >> 5, q = idx & 31;
         const float4 as = make_float4(a[j].x * s, a[j].y * s, a[j].z * s, a[j].w * s);
         uint2 hi, lo;
@@ -168,7 +171,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
       // B operand: hidden activations (32 edges x Hd)
       uint8_t* bh = sb + 2 * kWA;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < ((CGAT_EW_DBG & 2) ? 0 : 8); ++j) {
         const int idx = pl + kWGroup * j, r = idx >> 6, q = idx & 63;
         uint2 hi, lo;
         split_f16x4s(x[j], kF16LoScale, hi, lo);
@@ -191,6 +194,7 @@ __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArg
 #pragma unroll
         for (int ks = 0; ks < kWRows / 16; ++ks) {
           const uint32_t o = ks * 2048;
+          if (CGAT_EW_DBG & 1) continue;
           umma_f16_e(tmem + 256, umma_desc_mn_sw128_16b(a_lo + o, kWImg), umma_desc_mn_sw128_16b(b_hi + o, kWImg), idesc,
                    (ch | ks) != 0);
           umma_f16_e(tmem + 256, umma_desc_mn_sw128_16b(a_hi + o, kWImg), umma_desc_mn_sw128_16b(b_lo + o, kWImg), idesc, 1);
