@@ -164,6 +164,37 @@ def test_hyper_linear_fused_fwd_bwd(n, f16, monkeypatch):
     assert_close(bc.grad, bd.grad, "g_b", atol=1e-5 * bd.grad.abs().max().item() + 1e-4, rtol=1e-3)
 
 
+def test_hyper_linear_work_splits_agree():
+    """The f16 hyper kernels choose between two work decompositions (hyper_f16.cu): CTAs tied to one atom tile with a
+    slice of the output channels when there are enough SMs per tile, contiguous (tile, chunk) item ranges otherwise
+    (more than ~72 tile pairs: the 5 000-crystal inference batches).  The op is independent per atom row, so 20 000 atoms
+    in one call (item ranges) must reproduce the two 10 000-atom halves (tile-aligned): forward bit for bit — every row
+    sees the same MMA sequence either way — and the gradients to rounding (partial sums meet in a different order)."""
+    f, n = 128, 20000
+    g = torch.Generator().manual_seed(7)
+    z = torch.tanh(torch.randn(n, f, generator=g)).to(DEV)
+    y = torch.randn(n, f, generator=g).to(DEV)
+    w = (torch.randn(f * f + f, f, generator=g) * 0.0125).to(DEV)
+    b = (torch.randn(f * f + f, generator=g) * 0.09).to(DEV)
+    gw = torch.randn(n, f, generator=g).to(DEV)
+
+    def run(lo, hi):
+        zc, yc = z[lo:hi].clone().requires_grad_(True), y[lo:hi].clone().requires_grad_(True)
+        wc, bc = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+        out = ops.hyper_linear(zc, wc, bc, yc, f)
+        (out * gw[lo:hi]).sum().backward()
+        return out.detach(), zc.grad, yc.grad, wc.grad, bc.grad
+
+    whole = run(0, n)
+    a, c = run(0, n // 2), run(n // 2, n)
+    assert torch.equal(whole[0], torch.cat([a[0], c[0]])), "forward differs between the two work splits"
+    for i, name in ((1, "g_z"), (2, "g_y")):
+        assert_close(whole[i], torch.cat([a[i], c[i]]).double(), name, atol=2e-5, rtol=1e-5)
+    for i, name in ((3, "g_w"), (4, "g_b")):
+        ref = (a[i] + c[i]).double()
+        assert_close(whole[i], ref, name, atol=1e-5 * ref.abs().max().item(), rtol=1e-4)
+
+
 def test_pack_repack_on_weight_update():
     f = 128
     w = torch.randn(f * f + f, f, device=DEV) * 0.01
