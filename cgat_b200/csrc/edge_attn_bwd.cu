@@ -470,7 +470,9 @@ constexpr int kWStageBytes = 2 * kWAPart + 2 * kWBPart;  // 96 KB
 constexpr int kWStages = 2;
 constexpr int kWSmemBytes = kWStages * kWStageBytes + 2 * 3 * 32 * 4 + 256 + 1024;
 
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
+// max(x, 0.01 x): the same value as (x > 0 ? x : 0.01 x) for every x (signed zeros, infinities and NaN included), one
+// instruction less per hidden element in producers that are bound by their instruction stream
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, 0.01f * x); }
 
 __global__ void __launch_bounds__(kBThreads, 1) edge_wgrad_kernel(const WgradArgs g) {
   extern __shared__ uint8_t smem_raw[];

@@ -92,7 +92,9 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 
-__device__ __forceinline__ float lrelu(float x) { return x > 0.f ? x : 0.01f * x; }
+// max(x, 0.01 x): the same value as (x > 0 ? x : 0.01 x) for every x (signed zeros, infinities and NaN included), one
+// instruction less per hidden element in producers that are bound by their instruction stream
+__device__ __forceinline__ float lrelu(float x) { return fmaxf(x, 0.01f * x); }
 
 // exp(x) for x <= 0 on the SFU with fp32-level accuracy: ex2.approx (2^-22.5 relative) on the rounded product
 // x*log2(e), times (1 + residual*ln2) where the residual carries the rounding error of that product and the low

@@ -47,7 +47,7 @@ struct WArgs {
   int f, n_ch, n_kh;      // channels per head; 128-channel blocks per head; 256-wide blocks of the hidden units
 };
 
-__device__ __forceinline__ float lrelu_w(float x) { return x > 0.f ? x : 0.01f * x; }
+__device__ __forceinline__ float lrelu_w(float x) { return fmaxf(x, 0.01f * x); }   // == (x > 0 ? x : 0.01 x), one instruction less
 
 __global__ void __launch_bounds__(kWThreads, 1) edge_wgrad_f16_kernel(const WArgs g) {
   extern __shared__ uint8_t smem_raw[];
