@@ -718,8 +718,16 @@ using namespace cgat;
 extern "C" int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms) {
   // ~24 atoms per CTA: every CTA walks its atoms one after the other (index load -> row loads -> store), so the
   // memory-level parallelism comes from the number of resident CTAs (8+ per SM at 27 KB of shared memory each)
-  int64_t c = (n_atoms + 23) / 24;
-  return (int32_t)(c < 1 ? 1 : (c > 240 ? 240 : c));
+  // atoms per chunk, swept (profiles/r04y): 12 -> the reduce itself 303 us instead of 330, but the per-chunk rank partials
+  // (133 KB each) double and the partial sum that follows eats the gain; 48 / 96 -> 391 / 448 us
+#ifndef CGAT_SR_ATOMS
+#define CGAT_SR_ATOMS 24
+#endif
+#ifndef CGAT_SR_MAXCHUNKS
+#define CGAT_SR_MAXCHUNKS 240
+#endif
+  int64_t c = (n_atoms + CGAT_SR_ATOMS - 1) / CGAT_SR_ATOMS;
+  return (int32_t)(c < 1 ? 1 : (c > CGAT_SR_MAXCHUNKS ? CGAT_SR_MAXCHUNKS : c));
 }
 
 // Segment sums of the per-edge pre-activation gradients d_pre (E, cols; rows in destination order) that
