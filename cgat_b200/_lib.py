@@ -19,7 +19,7 @@ _lib = None
 
 _P, _I64, _I32, _F32, _SZ = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32, ctypes.c_float, ctypes.c_size_t
 
-ABI_VERSION = 6  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
+ABI_VERSION = 7  # CGAT_B200_ABI_VERSION in include/cgat_b200.h
 
 # name -> (restype, argtypes); must list every symbol declared in include/cgat_b200.h
 SIGNATURES = {
@@ -70,7 +70,9 @@ SIGNATURES = {
     "cgat_edge_attn_dgrad": (ctypes.c_int, [_P] * 10 + [_I64, _I32, _P, _I32, _P, _I64, _I64, _I32, _I32, _I32, _P]),
     "cgat_edge_attn_dgrad_f16": (ctypes.c_int, [_P] * 9 + [_I64, _I64, _I32, _I32, _I32, _P]),
     "cgat_edge_attn_reduce_chunks": (_I32, [_I64]),
-    "cgat_edge_attn_reduce": (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _I32, _I64, _I32, _P]),
+    "cgat_edge_attn_reduce_groups": (_I32, [_I64]),
+    "cgat_edge_attn_reduce_counters": (_I32, [_I64, _I32]),
+    "cgat_edge_attn_reduce": (ctypes.c_int, [_P, _I64, _P, _P, _P, _P, _P, _I64, _I32, _I32, _P, _P, _P, _I32, _I64, _I32, _P]),
     "cgat_edge_attn_wgrad_splits": (_I32, [_I32]),
     "cgat_edge_attn_wgrad": (ctypes.c_int, [_P] * 8 + [_I64, _I32, _I32, _I32, _P]),
     "cgat_sum_parts": (ctypes.c_int, [_P, _I32, _I64, _P, _I64, _I32, _P]),

@@ -642,10 +642,14 @@ struct ReduceArgs {
   float* G;
   int64_t ldd, ldg;
   int n_atoms, n_ranks, cols, n_chunks;
+  float* rank_out;         // (n_groups, n_ranks, cols): per-rank sums of kSRGroup consecutive chunks
+  int32_t* counters;       // (n_groups, column blocks), zeroed before the launch
 };
+constexpr int kSRGroup = 8;   // chunks whose per-rank partial sums are combined by the last CTA of the group to finish
 
 __global__ void __launch_bounds__(kSRThreads) edge_reduce_kernel(const ReduceArgs g) {
   extern __shared__ float4 sr_acc[];  // [n_ranks][kSRThreads]
+  __shared__ int s_last;
   // pass = lowest bit of blockIdx.y: the by-destination and the by-source CTA of one atom chunk are scheduled side by
   // side, and the out-edges of an atom end in its own crystal, i.e. in rows the neighbour CTA reads at about the same
   // time — part of the second read of d_pre (683 MB at the bench size, five times the L2) is then served by L2
@@ -707,6 +711,30 @@ __global__ void __launch_bounds__(kSRThreads) edge_reduce_kernel(const ReduceArg
       for (int r = 0; r < g.n_ranks; ++r)
         *reinterpret_cast<float4*>(ps.d_rank + ((int64_t)chunk * g.n_ranks + r) * g.cols + col) =
             sr_acc[r * kSRThreads + tid];
+    // The per-chunk partials (133 KB each at the default width) used to go to the caller as they were — 31 MB written
+    // and read again by the partial sum, and the reason smaller (faster) chunks did not pay (profiles/r04y).  Now the
+    // CTA that finishes LAST among the kSRGroup chunks of its group (same column block) adds the group's partials in
+    // chunk order — a fixed order whoever comes last, so still deterministic — while they are still in L2.
+    const int group = chunk / kSRGroup;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+      const int first = group * kSRGroup, members = min(kSRGroup, g.n_chunks - first);
+      s_last = atomicAdd(g.counters + (int64_t)group * gridDim.x + blockIdx.x, 1) == members - 1;
+    }
+    __syncthreads();
+    if (s_last && active) {
+      __threadfence();
+      const int first = group * kSRGroup, members = min(kSRGroup, g.n_chunks - first);
+      for (int r = 0; r < g.n_ranks; ++r) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int m = 0; m < members; ++m) {
+          const float4 v = __ldcg(reinterpret_cast<const float4*>(ps.d_rank + ((int64_t)(first + m) * g.n_ranks + r) * g.cols + col));
+          t.x += v.x, t.y += v.y, t.z += v.z, t.w += v.w;
+        }
+        *reinterpret_cast<float4*>(g.rank_out + ((int64_t)group * g.n_ranks + r) * g.cols + col) = t;
+      }
+    }
   }
 }
 
@@ -718,16 +746,24 @@ using namespace cgat;
 extern "C" int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms) {
   // ~24 atoms per CTA: every CTA walks its atoms one after the other (index load -> row loads -> store), so the
   // memory-level parallelism comes from the number of resident CTAs (8+ per SM at 27 KB of shared memory each)
-  // atoms per chunk, swept (profiles/r04y): 12 -> the reduce itself 303 us instead of 330, but the per-chunk rank partials
-  // (133 KB each) double and the partial sum that follows eats the gain; 48 / 96 -> 391 / 448 us
+  // atoms per chunk, swept (profiles/r04y): 12 / 24 / 48 / 96 -> 303 / 330 / 391 / 448 us for the reduce itself.  With
+  // one rank partial per chunk going back to the caller, 12 lost what it gained in the partial sum that follows; since
+  // the partials are combined per group of 8 chunks inside the kernel, the smaller chunk wins.
 #ifndef CGAT_SR_ATOMS
-#define CGAT_SR_ATOMS 24
+#define CGAT_SR_ATOMS 12
 #endif
 #ifndef CGAT_SR_MAXCHUNKS
-#define CGAT_SR_MAXCHUNKS 240
+#define CGAT_SR_MAXCHUNKS 4096
 #endif
   int64_t c = (n_atoms + CGAT_SR_ATOMS - 1) / CGAT_SR_ATOMS;
   return (int32_t)(c < 1 ? 1 : (c > CGAT_SR_MAXCHUNKS ? CGAT_SR_MAXCHUNKS : c));
+}
+// groups of chunks = parts of the d_rank result the caller sums; ints of the counter workspace
+extern "C" int32_t cgat_edge_attn_reduce_groups(int64_t n_atoms) {
+  return (cgat_edge_attn_reduce_chunks(n_atoms) + kSRGroup - 1) / kSRGroup;
+}
+extern "C" int32_t cgat_edge_attn_reduce_counters(int64_t n_atoms, int32_t cols) {
+  return cgat_edge_attn_reduce_groups(n_atoms) * (int32_t)ceil_div(cols, kSRCols);
 }
 
 // Segment sums of the per-edge pre-activation gradients d_pre (E, cols; rows in destination order) that
@@ -738,7 +774,8 @@ extern "C" int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms) {
 extern "C" int cgat_edge_attn_reduce(const float* d_pre, int64_t ldd, const int32_t* dst_rowptr,
                                      const int32_t* src_rowptr, const int32_t* src_row, const int32_t* src_rank,
                                      float* G, int64_t ldg, int32_t dst_col_off, int32_t src_col_off, float* d_rank,
-                                     int32_t n_ranks, int64_t n_atoms, int32_t cols, void* stream_) {
+                                     float* rank_scratch, int32_t* counters, int32_t n_ranks, int64_t n_atoms,
+                                     int32_t cols, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if ((cols & 3) || (ldd & 3) || (ldg & 3) || (dst_col_off & 3) || (src_col_off & 3))
     return fail(-2, "cgat_edge_attn_reduce: cols, ldd, ldg and the column offsets must be multiples of 4");
@@ -747,7 +784,11 @@ extern "C" int cgat_edge_attn_reduce(const float* d_pre, int64_t ldd, const int3
   const int n_chunks = cgat_edge_attn_reduce_chunks(n_atoms);
   ReduceArgs a{};
   a.pass[0] = ReducePass{dst_rowptr, nullptr, nullptr, nullptr, dst_col_off};
-  a.pass[1] = ReducePass{src_rowptr, src_row, src_rank, d_rank, src_col_off};
+  if (!d_rank || !rank_scratch || !counters || !src_rank)
+    return fail(-2, "cgat_edge_attn_reduce: d_rank, rank_scratch, counters and src_rank are required");
+  a.pass[1] = ReducePass{src_rowptr, src_row, src_rank, rank_scratch, src_col_off};
+  a.rank_out = d_rank, a.counters = counters;
+  CGAT_CUDA(cudaMemsetAsync(counters, 0, sizeof(int32_t) * cgat_edge_attn_reduce_counters(n_atoms, cols), stream));
   a.d_pre = d_pre, a.G = G, a.ldd = ldd, a.ldg = ldg;
   a.n_atoms = (int)n_atoms, a.n_ranks = n_ranks, a.cols = cols, a.n_chunks = n_chunks;
   const size_t smem = (size_t)n_ranks * kSRThreads * sizeof(float4);

@@ -762,14 +762,16 @@ class _EdgeAttentionFused(torch.autograd.Function):
                       n_ranks, _lib.ptr(d_pre), n, e, heads, f, hd_pad, st,
                       work=dict(key="edge_attn_dgrad", bound="tensor", flops=flops2))
         so = plan.by_source()
-        chunks = int(lib.cgat_edge_attn_reduce_chunks(n))
+        chunks, groups = int(lib.cgat_edge_attn_reduce_chunks(n)), int(lib.cgat_edge_attn_reduce_groups(n))
         d_p = torch.empty((n, 4 * hhd), dtype=torch.float32, device=dev)
-        d_rank = torch.empty((chunks, n_ranks, 2 * hhd), dtype=torch.float32, device=dev)
+        d_rank = torch.empty((groups, n_ranks, 2 * hhd), dtype=torch.float32, device=dev)
+        rank_scratch = torch.empty((chunks, n_ranks, 2 * hhd), dtype=torch.float32, device=dev)
+        counters = torch.empty(int(lib.cgat_edge_attn_reduce_counters(n, 2 * hhd)), dtype=torch.int32, device=dev)
         _lib.call("cgat_edge_attn_reduce", _lib.ptr(d_pre), 2 * hhd, _lib.ptr(plan.rowptr), _lib.ptr(so.rowptr),
-                  _lib.ptr(so.row), _lib.ptr(so.rank), _lib.ptr(d_p), 4 * hhd, 0, 2 * hhd, _lib.ptr(d_rank), n_ranks,
-                  n, 2 * hhd, st,
+                  _lib.ptr(so.row), _lib.ptr(so.rank), _lib.ptr(d_p), 4 * hhd, 0, 2 * hhd, _lib.ptr(d_rank),
+                  _lib.ptr(rank_scratch), _lib.ptr(counters), n_ranks, n, 2 * hhd, st,
                   work=dict(key="edge_attn_reduce", bound="hbm",
-                            bytes=4.0 * (2 * e * 2 * hhd + n * 4 * hhd + chunks * n_ranks * 2 * hhd),
+                            bytes=4.0 * (2 * e * 2 * hhd + n * 4 * hhd + groups * n_ranks * 2 * hhd),
                             note="reads d_pre twice (by destination, by source), writes dL/dP + per-rank partials"))
         del d_pre
         d_t = sum_parts(d_rank)                                                     # (K+1, 2*HHd)

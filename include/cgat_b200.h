@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define CGAT_B200_ABI_VERSION 6 /* 2: bwd_prep bias_sums; f16 entry points. 3: train-step glue. 4: dz_amax. 5: n_ranks, status flags. 6: parts_f16 */
+#define CGAT_B200_ABI_VERSION 7 /* 2: bwd_prep bias_sums; f16 entry points. 3: train-step glue. 4: dz_amax. 5: n_ranks, status flags. 6: parts_f16. 7: reduce workspace */
 
 int cgat_abi_version(void);
 const char* cgat_last_error(void);
@@ -264,12 +264,18 @@ int cgat_edge_attn_dgrad_f16(const float* d_gate, const float* d_msg, const uint
  * and a second tensor-core pass over source-grouped edges.
  *   G[a, dst_col_off:+cols] = sum over the in-edges of atom a;  G[a, src_col_off:+cols] = sum over its out-edges
  *   (src_rowptr / src_row / src_rank: the source-grouped order, src_row = row of d_pre);
- *   d_rank (cgat_edge_attn_reduce_chunks(N), n_ranks, cols): partial sums per shell rank (sum dim 0 = dL/dT). */
+ *   d_rank (cgat_edge_attn_reduce_groups(N), n_ranks, cols): partial sums per shell rank (sum dim 0 = dL/dT);
+ *   rank_scratch (cgat_edge_attn_reduce_chunks(N), n_ranks, cols) floats and counters
+ *   (cgat_edge_attn_reduce_counters(N, cols) int32, zeroed by the call): workspace — every CTA chunk leaves its
+ *   per-rank partial in the scratch and the last CTA of a group of chunks to finish adds the group's partials in
+ *   chunk order (deterministic) into d_rank.                                                                     */
 int32_t cgat_edge_attn_reduce_chunks(int64_t n_atoms);
+int32_t cgat_edge_attn_reduce_groups(int64_t n_atoms);
+int32_t cgat_edge_attn_reduce_counters(int64_t n_atoms, int32_t cols);
 int cgat_edge_attn_reduce(const float* d_pre, int64_t ldd, const int32_t* dst_rowptr, const int32_t* src_rowptr,
                           const int32_t* src_row, const int32_t* src_rank, float* G, int64_t ldg,
-                          int32_t dst_col_off, int32_t src_col_off, float* d_rank, int32_t n_ranks, int64_t n_atoms,
-                          int32_t cols, void* stream);
+                          int32_t dst_col_off, int32_t src_col_off, float* d_rank, float* rank_scratch,
+                          int32_t* counters, int32_t n_ranks, int64_t n_atoms, int32_t cols, void* stream);
 int32_t cgat_edge_attn_wgrad_splits(int32_t heads);
 int cgat_edge_attn_wgrad(const float* P, const float* T, const int32_t* src, const int32_t* dst,
                          const int32_t* rank, const float* d_gate, const float* d_msg, float* out,
