@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(kSRThreads) edge_reduce_kernel(const ReduceArg
   for (int a = a_lo; a < a_hi; ++a) {
     const int b = __ldg(ps.rowptr + a), e = __ldg(ps.rowptr + a + 1);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int t0 = b; t0 < e; t0 += 8) {
+    for (int t0 = b; t0 < e; t0 += 8) {   // (12 / 16 rows in flight per thread: 275 / 327 us against 267 — occupancy)
       float4 v[8];
       int rk[8];
 #pragma unroll
